@@ -1,0 +1,10 @@
+"""altro_cpp_b200 — B200-native batched AL-iLQR (host-side Python binding of the C ABI).
+
+The product is the CUDA library ``libaltro_b200.so`` (C ABI in include/altro_b200.h);
+this package only marshals arrays to it.  There is no CPU fallback: importing works
+anywhere, every compute call needs a CUDA device.
+"""
+from . import problems  # noqa: F401
+from .capi import BatchSolver, Options, default_options, lib, SolverError  # noqa: F401
+
+__all__ = ["problems", "BatchSolver", "Options", "default_options", "lib", "SolverError"]

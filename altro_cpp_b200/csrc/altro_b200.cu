@@ -1,0 +1,814 @@
+// altro_b200.cu — C ABI (include/altro_b200.h) over the kernels in kernels.cuh.
+//
+// Host side only marshals: it flattens the problem description into one blob, owns the device
+// arrays, converts between the instance-major API layout and the tile-major device layout and
+// launches kernels.  No numerical work of the hot path runs on the host and there is no CPU
+// fallback — without a usable CUDA device every compute entry point fails.
+#include "../../include/altro_b200.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace altro_b200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(ALTRO_B200_ERR_CUDA,                                                    \
+                  std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                      std::to_string(__LINE__) + ")");                                    \
+  } while (0)
+
+struct HostCost {
+  std::vector<double> data;  // Q, R, H, q, r, c
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// Problem (host description)
+// ------------------------------------------------------------------------------------------
+struct altro_b200_problem {
+  int n, m, N;
+  int model = kUnicycle;
+  std::vector<double> params;
+  std::vector<float> h, t;
+  std::vector<int> cost_id;            // per knot, -1 = unset
+  std::vector<HostCost> costs;
+  std::vector<std::vector<ConBlock>> eq, ineq;  // per knot, insertion order
+  std::vector<double> x0;
+  bool step_set = false, model_set = false;
+};
+
+namespace {
+
+// Flatten to the device blob.  use_constraints = false drops every constraint (plain iLQR).
+int build_blob(const altro_b200_problem& p, bool use_constraints, std::vector<char>* out,
+               int* pmax_out) {
+  const int n = p.n, m = p.m, N = p.N;
+  for (int k = 0; k <= N; ++k)
+    if (p.cost_id[k] < 0)
+      return fail(ALTRO_B200_ERR_STATE, "cost function of knot " + std::to_string(k) + " is not set");
+  if (!p.step_set) return fail(ALTRO_B200_ERR_STATE, "time step is not set");
+  if (!p.model_set) return fail(ALTRO_B200_ERR_STATE, "dynamics model is not set");
+  // constraint sets: dedupe identical knots
+  std::vector<ConSet> sets;
+  std::vector<int> conset_id(N + 1, 0);
+  int pmax = 0;
+  for (int k = 0; k <= N; ++k) {
+    ConSet cs;
+    std::memset(&cs, 0, sizeof(cs));
+    if (use_constraints) {
+      int row = 0;
+      for (const auto* vec : {&p.eq[k], &p.ineq[k]})
+        for (const ConBlock& b : *vec) {
+          if (cs.nblocks >= kMaxBlocks)
+            return fail(ALTRO_B200_ERR_UNSUPPORTED, "more than 4 constraints at one knot");
+          ConBlock c = b;
+          c.row0 = row;
+          row += c.p;
+          cs.blk[cs.nblocks++] = c;
+        }
+      cs.p_total = row;
+      pmax = std::max(pmax, row);
+    }
+    int id = -1;
+    for (size_t i = 0; i < sets.size(); ++i)
+      if (std::memcmp(&sets[i], &cs, sizeof(cs)) == 0) id = static_cast<int>(i);
+    if (id < 0) {
+      sets.push_back(cs);
+      id = static_cast<int>(sets.size()) - 1;
+    }
+    conset_id[k] = id;
+  }
+  const int cost_stride = n * n + m * m + n * m + n + m + 1;
+  auto align = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
+  BlobHeader h;
+  std::memset(&h, 0, sizeof(h));
+  h.n = n; h.m = m; h.N = N; h.model = p.model;
+  h.ncost = static_cast<int>(p.costs.size());
+  h.nconset = static_cast<int>(sets.size());
+  h.pmax = pmax;
+  h.nparams = static_cast<int>(p.params.size());
+  h.cost_stride = cost_stride;
+  size_t off = align(sizeof(BlobHeader), 16);
+  h.off_cost_id = static_cast<int>(off); off = align(off + sizeof(int) * (N + 1), 16);
+  h.off_conset_id = static_cast<int>(off); off = align(off + sizeof(int) * (N + 1), 16);
+  h.off_h = static_cast<int>(off); off = align(off + sizeof(float) * (N + 1), 16);
+  h.off_t = static_cast<int>(off); off = align(off + sizeof(float) * (N + 1), 16);
+  h.off_params = static_cast<int>(off); off = align(off + sizeof(double) * std::max<size_t>(1, p.params.size()), 16);
+  h.off_cost = static_cast<int>(off); off = align(off + sizeof(double) * cost_stride * p.costs.size(), 16);
+  h.off_conset = static_cast<int>(off); off = align(off + sizeof(ConSet) * sets.size(), 16);
+  h.bytes = static_cast<int>(off);
+  out->assign(off, 0);
+  char* b = out->data();
+  std::memcpy(b, &h, sizeof(h));
+  std::memcpy(b + h.off_cost_id, p.cost_id.data(), sizeof(int) * (N + 1));
+  std::memcpy(b + h.off_conset_id, conset_id.data(), sizeof(int) * (N + 1));
+  std::memcpy(b + h.off_h, p.h.data(), sizeof(float) * (N + 1));
+  std::memcpy(b + h.off_t, p.t.data(), sizeof(float) * (N + 1));
+  if (!p.params.empty())
+    std::memcpy(b + h.off_params, p.params.data(), sizeof(double) * p.params.size());
+  for (size_t i = 0; i < p.costs.size(); ++i)
+    std::memcpy(b + h.off_cost + sizeof(double) * cost_stride * i, p.costs[i].data.data(),
+                sizeof(double) * cost_stride);
+  std::memcpy(b + h.off_conset, sets.data(), sizeof(ConSet) * sets.size());
+  *pmax_out = pmax;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Kernel dispatch per device-capable model
+// ------------------------------------------------------------------------------------------
+struct Ops {
+  void (*solve)(const SolverParams&, int mode, int smem, cudaStream_t);
+  void (*phase)(const SolverParams&, int phase, int smem, cudaStream_t);
+  void (*expansions)(const SolverParams&, int smem, cudaStream_t);
+  cudaError_t (*backward_mat)(const SolverParams&, bool store_ctg, cudaStream_t);
+};
+
+constexpr int kBpStages = 4;
+
+template <class M>
+Ops make_ops() {
+  Ops o;
+  o.solve = [](const SolverParams& P, int mode, int smem, cudaStream_t st) {
+    k_solve<M><<<P.T, kTile, smem, st>>>(P, mode);
+  };
+  o.phase = [](const SolverParams& P, int phase, int smem, cudaStream_t st) {
+    k_phase<M><<<P.T, kTile, smem, st>>>(P, phase);
+  };
+  o.expansions = [](const SolverParams& P, int smem, cudaStream_t st) {
+    constexpr int kWarps = 4;
+    dim3 grid(P.T, (P.N + 1 + kWarps - 1) / kWarps);
+    k_update_expansions<M><<<grid, kWarps * kTile, smem, st>>>(P);
+  };
+  o.backward_mat = [](const SolverParams& P, bool store_ctg, cudaStream_t st) -> cudaError_t {
+    const int smem = kBpStages * Lane<M>::nexp * kTile * sizeof(double) + kBpStages * 8;
+    cudaError_t e;
+    if (store_ctg) {
+      e = cudaFuncSetAttribute(k_backward_mat<M, kBpStages, true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      k_backward_mat<M, kBpStages, true><<<P.T, kTile, smem, st>>>(P);
+    } else {
+      e = cudaFuncSetAttribute(k_backward_mat<M, kBpStages, false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      k_backward_mat<M, kBpStages, false><<<P.T, kTile, smem, st>>>(P);
+    }
+    return cudaGetLastError();
+  };
+  return o;
+}
+
+bool lookup_ops(int n, int m, int model, Ops* out) {
+  if (model == kUnicycle && n == 3 && m == 2) { if (out) *out = make_ops<Unicycle>(); return true; }
+  if (model == kTripleIntegrator && n == 6 && m == 2) { if (out) *out = make_ops<TripleIntegrator<2>>(); return true; }
+  if (model == kTripleIntegrator && n == 3 && m == 1) { if (out) *out = make_ops<TripleIntegrator<1>>(); return true; }
+  if (model == kCartpole && n == 4 && m == 1) { if (out) *out = make_ops<Cartpole>(); return true; }
+  return false;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// Solver
+// ------------------------------------------------------------------------------------------
+struct altro_b200_solver {
+  int n, m, N, B, T, Bp, pmax, device, use_al;
+  Ops ops;
+  SolverParams P;
+  char* d_blob = nullptr;
+  int blob_bytes = 0;
+  double* d_io = nullptr;   // staging for instance-major transfers
+  size_t io_bytes = 0;
+  size_t dev_bytes = 0;
+  int64_t launches = 0;
+  std::vector<void*> allocs;
+  bool inputs_set = false;
+
+  int alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    allocs.push_back(*p);
+    dev_bytes += bytes;
+    return 0;
+  }
+  int ensure_io(size_t bytes) {
+    if (bytes <= io_bytes) return 0;
+    if (d_io) { cudaFree(d_io); dev_bytes -= io_bytes; }
+    cudaError_t e = cudaMalloc(&d_io, bytes);
+    if (e != cudaSuccess) { d_io = nullptr; io_bytes = 0; return fail(ALTRO_B200_ERR_CUDA, "cudaMalloc(staging) failed"); }
+    io_bytes = bytes;
+    dev_bytes += bytes;
+    return 0;
+  }
+  int ensure_stepwise() {  // EXP / CTG / COSTS are only needed by the step-wise API
+    const size_t knots = static_cast<size_t>(T) * (N + 1) * kTile * sizeof(double);
+    if (!P.EXP) {
+      int rc;
+      if ((rc = alloc(reinterpret_cast<void**>(&P.EXP), knots * exp_fields(n, m)))) return rc;
+      if ((rc = alloc(reinterpret_cast<void**>(&P.CTG), knots * (n * n + n)))) return rc;
+      if ((rc = alloc(reinterpret_cast<void**>(&P.COSTS), knots))) return rc;
+      cudaMemset(P.EXP, 0, knots * exp_fields(n, m));
+      cudaMemset(P.CTG, 0, knots * (n * n + n));
+      cudaMemset(P.COSTS, 0, knots);
+    }
+    return 0;
+  }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+DevOptions to_dev(const altro_b200_options& o) {
+  DevOptions d;
+  std::memset(&d, 0, sizeof(d));
+  d.max_iterations_total = o.max_iterations_total;
+  d.max_iterations_outer = o.max_iterations_outer;
+  d.max_iterations_inner = o.max_iterations_inner;
+  d.bp_reg_fail_threshold = o.bp_reg_fail_threshold;
+  d.check_forwardpass_bounds = o.check_forwardpass_bounds;
+  d.line_search_max_iterations = o.line_search_max_iterations;
+  d.reset_duals = o.reset_duals;
+  d.cost_tolerance = o.cost_tolerance;
+  d.gradient_tolerance = o.gradient_tolerance;
+  d.bp_reg_increase_factor = o.bp_reg_increase_factor;
+  d.bp_reg_initial = o.bp_reg_initial;
+  d.bp_reg_max = o.bp_reg_max;
+  d.bp_reg_min = o.bp_reg_min;
+  d.state_max = o.state_max;
+  d.control_max = o.control_max;
+  d.line_search_lower_bound = o.line_search_lower_bound;
+  d.line_search_upper_bound = o.line_search_upper_bound;
+  d.line_search_decrease_factor = o.line_search_decrease_factor;
+  d.constraint_tolerance = o.constraint_tolerance;
+  d.maximum_penalty = o.maximum_penalty;
+  d.initial_penalty = o.initial_penalty;
+  d.penalty_scaling = o.penalty_scaling;
+  return d;
+}
+
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+int check_launch(altro_b200_solver* s, int nlaunch) {
+  s->launches += nlaunch;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(ALTRO_B200_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int fill_scalar(altro_b200_solver* s, int field, double v, cudaStream_t st) {
+  k_fill_scalar<<<(s->Bp + 255) / 256, 256, 0, st>>>(s->P.sc + static_cast<size_t>(field) * s->Bp, v, s->Bp);
+  return check_launch(s, 1);
+}
+int fill_int(altro_b200_solver* s, int field, int v, cudaStream_t st) {
+  k_fill_int<<<(s->Bp + 255) / 256, 256, 0, st>>>(s->P.is + static_cast<size_t>(field) * s->Bp, v, s->Bp);
+  return check_launch(s, 1);
+}
+
+// gather one tile-major array into instance-major staging, then to host
+int unpack_to(altro_b200_solver* s, const double* src0, const double* src1, int K, int F, int f0,
+              int nf, int k0, int nk, double* dst, bool dst_is_host, bool by_zsel,
+              cudaStream_t st) {
+  const size_t bytes = static_cast<size_t>(s->B) * nk * nf * sizeof(double);
+  double* d = dst;
+  if (dst_is_host) {
+    int rc = s->ensure_io(bytes);
+    if (rc) return rc;
+    d = s->d_io;
+  }
+  dim3 grid((s->B + 127) / 128, nk);
+  k_unpack<<<grid, 128, 0, st>>>(s->P, src0, src1, K, F, f0, nf, k0, nk, d, by_zsel ? 1 : 0);
+  int rc = check_launch(s, 1);
+  if (rc) return rc;
+  if (dst_is_host) {
+    CU(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ==========================================================================================
+extern "C" {
+
+const char* altro_b200_last_error(void) { return g_err.c_str(); }
+const char* altro_b200_version(void) { return "altro-cpp_b200 0.1.0 (sm_100a)"; }
+
+void altro_b200_default_options(altro_b200_options* o) {  // solver_options.hpp:23-56
+  std::memset(o, 0, sizeof(*o));
+  o->max_iterations_total = 300;
+  o->max_iterations_outer = 30;
+  o->max_iterations_inner = 100;
+  o->cost_tolerance = 1e-4;
+  o->gradient_tolerance = 1e-2;
+  o->bp_reg_increase_factor = 1.6;
+  o->bp_reg_initial = 0.0;
+  o->bp_reg_max = 1e8;
+  o->bp_reg_min = 1e-8;
+  o->bp_reg_fail_threshold = 100;
+  o->check_forwardpass_bounds = 1;
+  o->state_max = 1e8;
+  o->control_max = 1e8;
+  o->line_search_max_iterations = 20;
+  o->line_search_lower_bound = 1e-8;
+  o->line_search_upper_bound = 10.0;
+  o->line_search_decrease_factor = 2;
+  o->constraint_tolerance = 1e-4;
+  o->maximum_penalty = 1e8;
+  o->initial_penalty = 1.0;
+  o->reset_duals = 1;
+  o->penalty_scaling = 10.0;
+}
+
+int altro_b200_is_supported(int n, int m, int model) { return lookup_ops(n, m, model, nullptr) ? 1 : 0; }
+
+// ---------------------------------------------------------------- problem
+int altro_b200_problem_create(int n, int m, int N, altro_b200_problem** out) {
+  if (!out || n <= 0 || m <= 0 || N <= 0 || n > kMaxDim || m > kMaxDim)
+    return fail(ALTRO_B200_ERR_ARG, "problem_create: bad dimensions");
+  auto* p = new altro_b200_problem();
+  p->n = n; p->m = m; p->N = N;
+  p->h.assign(N + 1, 0.f);
+  p->t.assign(N + 1, 0.f);
+  p->cost_id.assign(N + 1, -1);
+  p->eq.resize(N + 1);
+  p->ineq.resize(N + 1);
+  p->x0.assign(n, 0.0);
+  *out = p;
+  return 0;
+}
+void altro_b200_problem_destroy(altro_b200_problem* p) { delete p; }
+
+int altro_b200_problem_set_model(altro_b200_problem* p, int model, const double* params, int nparams) {
+  if (!p || nparams < 0 || (nparams > 0 && !params)) return fail(ALTRO_B200_ERR_ARG, "set_model: bad argument");
+  if (model == kCartpole && nparams != 4) return fail(ALTRO_B200_ERR_ARG, "cartpole needs params mc, mp, l, g");
+  p->model = model;
+  p->params.assign(params, params + nparams);
+  p->model_set = true;
+  return 0;
+}
+int altro_b200_problem_set_uniform_step(altro_b200_problem* p, float h) {
+  if (!p) return fail(ALTRO_B200_ERR_ARG, "null problem");
+  for (int k = 0; k < p->N; ++k) {  // trajectory.hpp:122-130
+    p->h[k] = h;
+    p->t[k] = static_cast<float>(k) * h;
+  }
+  p->h[p->N] = 0.0f;
+  p->t[p->N] = static_cast<float>(h) * p->N;
+  p->step_set = true;
+  return 0;
+}
+int altro_b200_problem_set_cost(altro_b200_problem* p, int k0, int k1, const double* Q, const double* R,
+                                const double* H, const double* q, const double* r, double c) {
+  if (!p || !Q || !R || !H || !q || !r) return fail(ALTRO_B200_ERR_ARG, "set_cost: null argument");
+  if (k0 < 0 || k1 > p->N + 1 || k0 >= k1) return fail(ALTRO_B200_ERR_ARG, "set_cost: bad knot range");
+  const int n = p->n, m = p->m;
+  HostCost hc;
+  hc.data.insert(hc.data.end(), Q, Q + n * n);
+  hc.data.insert(hc.data.end(), R, R + m * m);
+  hc.data.insert(hc.data.end(), H, H + n * m);
+  hc.data.insert(hc.data.end(), q, q + n);
+  hc.data.insert(hc.data.end(), r, r + m);
+  hc.data.push_back(c);
+  int id = -1;
+  for (size_t i = 0; i < p->costs.size(); ++i)
+    if (p->costs[i].data == hc.data) id = static_cast<int>(i);
+  if (id < 0) {
+    p->costs.push_back(hc);
+    id = static_cast<int>(p->costs.size()) - 1;
+  }
+  for (int k = k0; k < k1; ++k) p->cost_id[k] = id;
+  return 0;
+}
+int altro_b200_problem_add_goal(altro_b200_problem* p, int k, const double* xf) {
+  if (!p || !xf || k < 0 || k > p->N) return fail(ALTRO_B200_ERR_ARG, "add_goal: bad argument");
+  ConBlock b;
+  std::memset(&b, 0, sizeof(b));
+  b.kind = kGoal;
+  b.equality = 1;
+  b.p = p->n;
+  for (int i = 0; i < p->n; ++i) b.a[i] = xf[i];
+  p->eq[k].push_back(b);
+  return 0;
+}
+int altro_b200_problem_add_control_bound(altro_b200_problem* p, int k, const double* lb, const double* ub) {
+  if (!p || !lb || !ub || k < 0 || k > p->N) return fail(ALTRO_B200_ERR_ARG, "add_control_bound: bad argument");
+  ConBlock b;
+  std::memset(&b, 0, sizeof(b));
+  b.kind = kControlBound;
+  b.equality = 0;
+  int row = 0;
+  for (int i = 0; i < p->m; ++i) {
+    if (lb[i] > ub[i]) return fail(ALTRO_B200_ERR_ARG, "Lower bound isn't less than the upper bound.");
+    if (std::fabs(lb[i]) < DBL_MAX) {  // basic_constraints.hpp:136-143
+      b.idx[row] = i;
+      b.a[row] = lb[i];
+      ++row;
+    }
+  }
+  b.nl = row;
+  for (int i = 0; i < p->m; ++i)
+    if (std::fabs(ub[i]) < DBL_MAX) {
+      b.idx[row] = i;
+      b.a[row] = ub[i];
+      ++row;
+    }
+  b.nu = row - b.nl;
+  b.p = row;
+  if (row > kMaxDim) return fail(ALTRO_B200_ERR_UNSUPPORTED, "too many bound rows");
+  p->ineq[k].push_back(b);
+  return 0;
+}
+int altro_b200_problem_add_circles(altro_b200_problem* p, int k, int nc, const double* cx, const double* cy,
+                                   const double* cr, int xi, int yi) {
+  if (!p || !cx || !cy || !cr || k < 0 || k > p->N || nc <= 0 || nc > kMaxDim || xi < 0 || yi < 0 ||
+      xi >= p->n || yi >= p->n)
+    return fail(ALTRO_B200_ERR_ARG, "add_circles: bad argument");
+  ConBlock b;
+  std::memset(&b, 0, sizeof(b));
+  b.kind = kCircle;
+  b.equality = 0;
+  b.p = nc;
+  b.xi = xi;
+  b.yi = yi;
+  for (int i = 0; i < nc; ++i) {
+    b.a[i] = cx[i];
+    b.b[i] = cy[i];
+    b.c[i] = cr[i];
+  }
+  p->ineq[k].push_back(b);
+  return 0;
+}
+int altro_b200_problem_set_initial_state(altro_b200_problem* p, const double* x0) {
+  if (!p || !x0) return fail(ALTRO_B200_ERR_ARG, "set_initial_state: null argument");
+  p->x0.assign(x0, x0 + p->n);
+  return 0;
+}
+
+// ---------------------------------------------------------------- solver
+int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_constraints, int device,
+                             altro_b200_solver** out) {
+  if (!p || !out || batch <= 0) return fail(ALTRO_B200_ERR_ARG, "solver_create: bad argument");
+  Ops ops;
+  if (!lookup_ops(p->n, p->m, p->model, &ops))
+    return fail(ALTRO_B200_ERR_UNSUPPORTED, "no device instantiation for (n=" + std::to_string(p->n) + ", m=" +
+                                               std::to_string(p->m) + ", model=" + std::to_string(p->model) + ")");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev)
+    return fail(ALTRO_B200_ERR_CUDA, "no usable CUDA device (there is no CPU fallback)");
+  std::vector<char> blob;
+  int pmax = 0;
+  int rc = build_blob(*p, use_constraints != 0, &blob, &pmax);
+  if (rc) return rc;
+  DeviceGuard guard(device);
+  auto s = std::make_unique<altro_b200_solver>();
+  s->n = p->n; s->m = p->m; s->N = p->N; s->B = batch;
+  s->T = (batch + kTile - 1) / kTile;
+  s->Bp = s->T * kTile;
+  s->pmax = pmax;
+  s->device = device;
+  s->use_al = use_constraints != 0;
+  s->ops = ops;
+  std::memset(&s->P, 0, sizeof(s->P));
+  SolverParams& P = s->P;
+  P.B = batch; P.T = s->T; P.N = p->N; P.n = p->n; P.m = p->m; P.pmax = pmax; P.use_al = s->use_al;
+  const size_t knots = static_cast<size_t>(s->T) * (p->N + 1) * kTile * sizeof(double);
+  const int nz = p->n + p->m, nkd = p->m * p->n + p->m;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&s->d_blob), blob.size()))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&P.Z[0]), knots * nz))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&P.Z[1]), knots * nz))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&P.KD), knots * nkd))) return rc;
+  if (pmax > 0 && (rc = s->alloc(reinterpret_cast<void**>(&P.LAM), knots * pmax))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&P.X0), static_cast<size_t>(s->Bp) * p->n * sizeof(double)))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&P.sc), static_cast<size_t>(S_NUM) * s->Bp * sizeof(double)))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&P.is), static_cast<size_t>(I_NUM) * s->Bp * sizeof(int)))) return rc;
+  CU(cudaMemcpy(s->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  s->blob_bytes = static_cast<int>(blob.size());
+  P.blob = s->d_blob;
+  P.blob_bytes = s->blob_bytes;
+  CU(cudaMemset(P.Z[0], 0, knots * nz));
+  CU(cudaMemset(P.Z[1], 0, knots * nz));
+  CU(cudaMemset(P.KD, 0, knots * nkd));  // KnotPointFunctions::Init :271-278
+  if (pmax > 0) CU(cudaMemset(P.LAM, 0, knots * pmax));
+  CU(cudaMemset(P.X0, 0, static_cast<size_t>(s->Bp) * p->n * sizeof(double)));
+  CU(cudaMemset(P.sc, 0, static_cast<size_t>(S_NUM) * s->Bp * sizeof(double)));
+  CU(cudaMemset(P.is, 0, static_cast<size_t>(I_NUM) * s->Bp * sizeof(int)));
+  altro_b200_options o;
+  altro_b200_default_options(&o);
+  P.opt = to_dev(o);
+  if ((rc = fill_scalar(s.get(), S_PENALTY, 1.0, 0))) return rc;   // constraint_values.hpp:45 penalty_.setOnes
+  if ((rc = fill_scalar(s.get(), S_CSRC_ALPHA, -1.0, 0))) return rc;
+  if ((rc = fill_int(s.get(), I_STATUS, kUnsolved, 0))) return rc;
+  if ((rc = fill_int(s.get(), I_STATUS_AL, kUnsolved, 0))) return rc;
+  CU(cudaDeviceSynchronize());
+  *out = s.release();
+  return 0;
+}
+
+void altro_b200_solver_destroy(altro_b200_solver* s) {
+  if (!s) return;
+  DeviceGuard guard(s->device);
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->d_io) cudaFree(s->d_io);
+  delete s;
+}
+
+int altro_b200_solver_set_options(altro_b200_solver* s, const altro_b200_options* o) {
+  if (!s || !o) return fail(ALTRO_B200_ERR_ARG, "set_options: null argument");
+  s->P.opt = to_dev(*o);
+  return 0;
+}
+int altro_b200_solver_batch(const altro_b200_solver* s) { return s ? s->B : 0; }
+
+static int set_inputs_impl(altro_b200_solver* s, const double* x0_dev, const double* U0_dev,
+                           const double* u_nominal, cudaStream_t st) {
+  Unom un;
+  std::memset(&un, 0, sizeof(un));
+  if (!U0_dev) {
+    if (!u_nominal) return fail(ALTRO_B200_ERR_ARG, "set_inputs: need U0 or u_nominal");
+    for (int i = 0; i < s->m; ++i) un.v[i] = u_nominal[i];
+  }
+  dim3 grid((s->Bp + 127) / 128, s->N + 1);
+  k_pack_inputs<<<grid, 128, 0, st>>>(s->P, x0_dev, U0_dev, un);
+  s->inputs_set = true;
+  return check_launch(s, 1);
+}
+
+int altro_b200_solver_set_inputs_host(altro_b200_solver* s, const double* x0, const double* U0,
+                                      const double* u_nominal, void* stream) {
+  if (!s || !x0) return fail(ALTRO_B200_ERR_ARG, "set_inputs: null argument");
+  DeviceGuard guard(s->device);
+  const size_t bx = static_cast<size_t>(s->B) * s->n * sizeof(double);
+  const size_t bu = U0 ? static_cast<size_t>(s->B) * s->N * s->m * sizeof(double) : 0;
+  int rc = s->ensure_io(bx + bu);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(s->d_io, x0, bx, cudaMemcpyHostToDevice, S(stream)));
+  double* dU = nullptr;
+  if (U0) {
+    dU = s->d_io + static_cast<size_t>(s->B) * s->n;
+    CU(cudaMemcpyAsync(dU, U0, bu, cudaMemcpyHostToDevice, S(stream)));
+  }
+  return set_inputs_impl(s, s->d_io, dU, u_nominal, S(stream));
+}
+int altro_b200_solver_set_inputs_dev(altro_b200_solver* s, const double* x0_dev, const double* U0_dev,
+                                     const double* u_nominal, void* stream) {
+  if (!s || !x0_dev) return fail(ALTRO_B200_ERR_ARG, "set_inputs: null argument");
+  DeviceGuard guard(s->device);
+  return set_inputs_impl(s, x0_dev, U0_dev, u_nominal, S(stream));
+}
+int altro_b200_solver_set_states_host(altro_b200_solver* s, const double* X, void* stream) {
+  if (!s || !X) return fail(ALTRO_B200_ERR_ARG, "set_states: null argument");
+  DeviceGuard guard(s->device);
+  const size_t bytes = static_cast<size_t>(s->B) * (s->N + 1) * s->n * sizeof(double);
+  int rc = s->ensure_io(bytes);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(s->d_io, X, bytes, cudaMemcpyHostToDevice, S(stream)));
+  dim3 grid((s->B + 127) / 128, s->N + 1);
+  k_set_states<<<grid, 128, 0, S(stream)>>>(s->P, s->d_io);
+  return check_launch(s, 1);
+}
+int altro_b200_solver_set_penalty(altro_b200_solver* s, double rho, void* stream) {
+  if (!s || !(rho >= 0)) return fail(ALTRO_B200_ERR_ARG, "Penalty must be positive.");
+  DeviceGuard guard(s->device);
+  return fill_scalar(s, S_PENALTY, rho, S(stream));
+}
+int altro_b200_solver_set_duals_host(altro_b200_solver* s, int k, const double* lambda, int p, void* stream) {
+  if (!s || !lambda || k < 0 || k > s->N || p < 0 || p > s->pmax)
+    return fail(ALTRO_B200_ERR_ARG, "set_duals: bad argument");
+  DeviceGuard guard(s->device);
+  int rc = s->ensure_io(sizeof(double) * kMaxDim * kMaxBlocks);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(s->d_io, lambda, sizeof(double) * p, cudaMemcpyHostToDevice, S(stream)));
+  k_fill_duals<<<(s->Bp + 127) / 128, 128, 0, S(stream)>>>(s->P, k, s->d_io, p);
+  return check_launch(s, 1);
+}
+
+// ---------------------------------------------------------------- solves
+static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
+  DeviceGuard guard(s->device);
+  s->ops.solve(s->P, mode, s->blob_bytes, st);
+  return check_launch(s, 1);
+}
+int altro_b200_solve_al(altro_b200_solver* s, void* stream) { return solve_impl(s, 1, S(stream)); }
+int altro_b200_solve_ilqr(altro_b200_solver* s, void* stream) { return solve_impl(s, 0, S(stream)); }
+
+int altro_b200_solve_al_host(altro_b200_solver* s, const double* x0, const double* U0, const double* u_nominal,
+                             double* X, double* U, double* cost, double* viol, int32_t* status,
+                             int32_t* iters, void* stream) {
+  int rc = altro_b200_solver_set_inputs_host(s, x0, U0, u_nominal, stream);
+  if (rc) return rc;
+  if ((rc = altro_b200_solve_al(s, stream))) return rc;
+  if (X || U)
+    if ((rc = altro_b200_get_trajectory_host(s, X, U, stream))) return rc;
+  return altro_b200_get_results_host(s, cost, viol, status, iters, stream);
+}
+
+// ---------------------------------------------------------------- step-wise phases
+static int phase_impl(altro_b200_solver* s, int phase, cudaStream_t st) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
+  DeviceGuard guard(s->device);
+  int rc = s->ensure_stepwise();
+  if (rc) return rc;
+  s->ops.phase(s->P, phase, s->blob_bytes, st);
+  return check_launch(s, 1);
+}
+int altro_b200_rollout(altro_b200_solver* s, void* stream) { return phase_impl(s, kPhaseRollout, S(stream)); }
+int altro_b200_cost(altro_b200_solver* s, void* stream) { return phase_impl(s, kPhaseCost, S(stream)); }
+int altro_b200_update_expansions(altro_b200_solver* s, void* stream) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
+  DeviceGuard guard(s->device);
+  int rc = s->ensure_stepwise();
+  if (rc) return rc;
+  s->ops.expansions(s->P, s->blob_bytes, S(stream));
+  return check_launch(s, 1);
+}
+int altro_b200_backward_pass(altro_b200_solver* s, void* stream) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  if (!s->P.EXP) return fail(ALTRO_B200_ERR_STATE, "UpdateExpansions must run before BackwardPass");
+  DeviceGuard guard(s->device);
+  cudaError_t e = s->ops.backward_mat(s->P, /*store_ctg=*/true, S(stream));
+  s->launches += 1;
+  if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("backward_pass: ") + cudaGetErrorString(e));
+  return 0;
+}
+int altro_b200_forward_pass(altro_b200_solver* s, void* stream) { return phase_impl(s, kPhaseForward, S(stream)); }
+int altro_b200_update_convergence_statistics(altro_b200_solver* s, void* stream) {
+  return phase_impl(s, kPhaseStats, S(stream));
+}
+int altro_b200_update_duals(altro_b200_solver* s, void* stream) { return phase_impl(s, kPhaseDuals, S(stream)); }
+int altro_b200_update_penalties(altro_b200_solver* s, void* stream) {
+  return phase_impl(s, kPhasePenalties, S(stream));
+}
+
+// Measurement entry points (not part of the reference surface): the bare kernels.
+int altro_b200_backward_pass_stream_only(altro_b200_solver* s, void* stream) {
+  if (!s || !s->P.EXP) return fail(ALTRO_B200_ERR_STATE, "UpdateExpansions must run before BackwardPass");
+  DeviceGuard guard(s->device);
+  cudaError_t e = s->ops.backward_mat(s->P, /*store_ctg=*/false, S(stream));
+  s->launches += 1;
+  if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("backward_pass: ") + cudaGetErrorString(e));
+  return 0;
+}
+int altro_b200_backward_pass_fused(altro_b200_solver* s, void* stream) {
+  return phase_impl(s, kPhaseBackwardFused, S(stream));
+}
+int altro_b200_solve_setup(altro_b200_solver* s, void* stream) { return phase_impl(s, kPhaseSolveSetup, S(stream)); }
+
+// ---------------------------------------------------------------- outputs
+int altro_b200_get_trajectory_host(altro_b200_solver* s, double* X, double* U, void* stream) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  DeviceGuard guard(s->device);
+  const int nz = s->n + s->m;
+  int rc;
+  if (X && (rc = unpack_to(s, s->P.Z[0], s->P.Z[1], s->N + 1, nz, 0, s->n, 0, s->N + 1, X, true, true, S(stream)))) return rc;
+  if (U && (rc = unpack_to(s, s->P.Z[0], s->P.Z[1], s->N + 1, nz, s->n, s->m, 0, s->N, U, true, true, S(stream)))) return rc;
+  return 0;
+}
+int altro_b200_get_trajectory_dev(altro_b200_solver* s, double* X, double* U, void* stream) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  DeviceGuard guard(s->device);
+  const int nz = s->n + s->m;
+  int rc;
+  if (X && (rc = unpack_to(s, s->P.Z[0], s->P.Z[1], s->N + 1, nz, 0, s->n, 0, s->N + 1, X, false, true, S(stream)))) return rc;
+  if (U && (rc = unpack_to(s, s->P.Z[0], s->P.Z[1], s->N + 1, nz, s->n, s->m, 0, s->N, U, false, true, S(stream)))) return rc;
+  return 0;
+}
+int altro_b200_get_gains_host(altro_b200_solver* s, double* K, double* d, void* stream) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  DeviceGuard guard(s->device);
+  const int nkd = s->m * s->n + s->m;
+  int rc;
+  if (K && (rc = unpack_to(s, s->P.KD, nullptr, s->N, nkd, 0, s->m * s->n, 0, s->N, K, true, false, S(stream)))) return rc;
+  if (d && (rc = unpack_to(s, s->P.KD, nullptr, s->N, nkd, s->m * s->n, s->m, 0, s->N, d, true, false, S(stream)))) return rc;
+  return 0;
+}
+int altro_b200_get_ctg_host(altro_b200_solver* s, int k, double* Pm, double* p, void* stream) {
+  if (!s || k < 0 || k > s->N) return fail(ALTRO_B200_ERR_ARG, "get_ctg: bad argument");
+  if (!s->P.CTG) return fail(ALTRO_B200_ERR_STATE, "BackwardPass has not run");
+  DeviceGuard guard(s->device);
+  const int F = s->n * s->n + s->n;
+  int rc;
+  if (Pm && (rc = unpack_to(s, s->P.CTG, nullptr, s->N + 1, F, 0, s->n * s->n, k, 1, Pm, true, false, S(stream)))) return rc;
+  if (p && (rc = unpack_to(s, s->P.CTG, nullptr, s->N + 1, F, s->n * s->n, s->n, k, 1, p, true, false, S(stream)))) return rc;
+  return 0;
+}
+int altro_b200_get_expansion_host(altro_b200_solver* s, int k, double* A, double* Bm, double* lxx, double* lxu,
+                                  double* luu, double* lx, double* lu, void* stream) {
+  if (!s || k < 0 || k > s->N) return fail(ALTRO_B200_ERR_ARG, "get_expansion: bad argument");
+  if (!s->P.EXP) return fail(ALTRO_B200_ERR_STATE, "UpdateExpansions has not run");
+  DeviceGuard guard(s->device);
+  const int n = s->n, m = s->m, F = exp_fields(n, m);
+  double* outs[7] = {A, Bm, lxx, lxu, luu, lx, lu};
+  const int sizes[7] = {n * n, n * m, n * n, n * m, m * m, n, m};
+  int f0 = 0;
+  for (int i = 0; i < 7; ++i) {
+    if (outs[i]) {
+      int rc = unpack_to(s, s->P.EXP, nullptr, s->N + 1, F, f0, sizes[i], k, 1, outs[i], true, false, S(stream));
+      if (rc) return rc;
+    }
+    f0 += sizes[i];
+  }
+  return 0;
+}
+int altro_b200_get_duals_host(altro_b200_solver* s, int k, double* lambda, int* p_out, void* stream) {
+  if (!s || k < 0 || k > s->N) return fail(ALTRO_B200_ERR_ARG, "get_duals: bad argument");
+  DeviceGuard guard(s->device);
+  if (p_out) *p_out = s->pmax;
+  if (lambda && s->pmax > 0)
+    return unpack_to(s, s->P.LAM, nullptr, s->N + 1, s->pmax, 0, s->pmax, k, 1, lambda, true, false, S(stream));
+  return 0;
+}
+int altro_b200_get_results_host(altro_b200_solver* s, double* cost, double* viol, int32_t* status,
+                                int32_t* iters, void* stream) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  DeviceGuard guard(s->device);
+  const size_t Bp = s->Bp, B = s->B;
+  cudaStream_t st = S(stream);
+  if (cost) CU(cudaMemcpyAsync(cost, s->P.sc + S_COST * Bp, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (viol) CU(cudaMemcpyAsync(viol, s->P.sc + S_VIOL * Bp, B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (status)
+    CU(cudaMemcpyAsync(status, s->P.is + (s->use_al ? I_STATUS_AL : I_STATUS) * Bp, B * sizeof(int),
+                       cudaMemcpyDeviceToHost, st));
+  std::vector<int> tmp;
+  if (iters) {
+    tmp.resize(3 * B);
+    for (int f = 0; f < 3; ++f)
+      CU(cudaMemcpyAsync(tmp.data() + f * B, s->P.is + (I_ITERS_INNER + f) * Bp, B * sizeof(int),
+                         cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  if (iters)
+    for (size_t b = 0; b < B; ++b)
+      for (int f = 0; f < 3; ++f) iters[3 * b + f] = tmp[f * B + b];
+  return 0;
+}
+int altro_b200_get_ilqr_status_host(altro_b200_solver* s, int32_t* status, void* stream) {
+  if (!s || !status) return fail(ALTRO_B200_ERR_ARG, "null argument");
+  DeviceGuard guard(s->device);
+  CU(cudaMemcpyAsync(status, s->P.is + static_cast<size_t>(I_STATUS) * s->Bp, s->B * sizeof(int),
+                     cudaMemcpyDeviceToHost, S(stream)));
+  CU(cudaStreamSynchronize(S(stream)));
+  return 0;
+}
+int altro_b200_get_scalars_host(altro_b200_solver* s, double* reg, double* dV0, double* dV1, double* alpha,
+                                double* z, double* dJ, double* grad, double* penalty, double* initial_cost,
+                                void* stream) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  DeviceGuard guard(s->device);
+  double* outs[9] = {reg, dV0, dV1, alpha, z, dJ, grad, penalty, initial_cost};
+  const int fields[9] = {S_REG, S_DV0, S_DV1, S_ALPHA, S_ZRATIO, S_DJ, S_GRAD, S_PENALTY, S_INITIAL_COST};
+  for (int i = 0; i < 9; ++i)
+    if (outs[i])
+      CU(cudaMemcpyAsync(outs[i], s->P.sc + static_cast<size_t>(fields[i]) * s->Bp, s->B * sizeof(double),
+                         cudaMemcpyDeviceToHost, S(stream)));
+  CU(cudaStreamSynchronize(S(stream)));
+  return 0;
+}
+
+size_t altro_b200_backward_pass_bytes(const altro_b200_solver* s) {
+  if (!s) return 0;
+  const size_t n = s->n, m = s->m, N = s->N;
+  const size_t per = 8 * (N * (n * (n + m) + n * n + n * m + m * m + n + m + m * n + m) + n * n + n);
+  return per * s->B;
+}
+int64_t altro_b200_kernel_launches(const altro_b200_solver* s) { return s ? s->launches : 0; }
+size_t altro_b200_device_bytes(const altro_b200_solver* s) { return s ? s->dev_bytes : 0; }
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+// common.cuh — problem descriptor, batch layout and per-instance state shared by the
+// kernels (kernels.cuh) and the C ABI (altro_b200.cu).
+//
+// Batch layout ("tile-major"): the batch is cut into tiles of 32 instances, one instance
+// per lane of a warp.  Every per-knot quantity is stored as
+//
+//     arr[tile][knot][field][lane]          (lane fastest, 32 doubles = 256 B per row)
+//
+// so a warp-wide access to one field of one knot is one fully coalesced 256 B request, and
+// the whole record of a (tile, knot) is one contiguous block (F*256 B) that a single
+// cp.async.bulk (TMA 1-D bulk copy) can stage into shared memory.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace altro_b200 {
+
+constexpr int kTile = 32;       // instances per tile (= warp size)
+constexpr int kMaxDim = 32;     // max rows of one constraint block (and max n)
+constexpr int kMaxBlocks = 4;   // constraint blocks per knot (ALCost eq_ + ineq_ entries)
+constexpr unsigned kFull = 0xffffffffu;
+
+enum ModelKind : int { kUnicycle = 0, kTripleIntegrator = 1, kCartpole = 2, kLinear = 3 };
+enum ConKind : int { kGoal = 0, kControlBound = 1, kCircle = 2 };
+
+// altro/common/solver_stats.hpp:20-31
+enum Status : int {
+  kSolved = 0,
+  kUnsolved = 1,
+  kStateLimit = 2,
+  kControlLimit = 3,
+  kCostIncrease = 4,
+  kMaxIterations = 5,
+  kMaxOuterIterations = 6,
+  kMaxInnerIterations = 7,
+  kMaxPenalty = 8,
+  kBackwardPassRegularizationFailed = 9,
+};
+
+// One ConstraintValues<n,m,ConType> (altro/constraints/constraint_values.hpp:24) of a knot.
+struct ConBlock {
+  int kind;      // ConKind
+  int equality;  // 1: ZeroCone (dual cone = identity); 0: NegativeOrthant
+  int p;         // OutputDimension()
+  int row0;      // first dual row of this block inside the knot's dual column
+  int nl, nu;    // control bound: number of lower / upper rows (basic_constraints.hpp:94-96)
+  int xi, yi;    // circle: state indices of the position (obstacle_constraints.hpp:89-94)
+  int idx[kMaxDim];   // control bound: control index of row i
+  double a[kMaxDim];  // goal: xf | bound: bound value of row i | circle: cx
+  double b[kMaxDim];  // circle: cy
+  double c[kMaxDim];  // circle: r
+};
+
+// The constraints of one knot in ALCost order: equalities then inequalities
+// (altro/augmented_lagrangian/al_cost.hpp:264-273).
+struct ConSet {
+  int nblocks;
+  int p_total;
+  ConBlock blk[kMaxBlocks];
+};
+
+// Header of the problem blob.  All offsets are bytes from the start of the blob; the blob is
+// copied verbatim into shared memory by every CTA.
+struct BlobHeader {
+  int n, m, N, model;
+  int ncost, nconset, pmax, nparams;
+  int cost_stride;     // doubles per QuadraticCost: n*n + m*m + n*m + n + m + 1
+  int off_cost_id;     // int[N+1]
+  int off_conset_id;   // int[N+1]
+  int off_h;           // float[N+1]
+  int off_t;           // float[N+1]
+  int off_params;      // double[nparams]
+  int off_cost;        // double[ncost*cost_stride]  (Q, R, H col-major, q, r, c)
+  int off_conset;      // ConSet[nconset]
+  int bytes;
+  int _pad;
+};
+
+// Device view of a blob.
+struct Desc {
+  const char* base;
+  __device__ __forceinline__ explicit Desc(const char* b) : base(b) {}
+  __device__ __forceinline__ const BlobHeader& hdr() const {
+    return *reinterpret_cast<const BlobHeader*>(base);
+  }
+  __device__ __forceinline__ const double* cost(int k) const {
+    const BlobHeader& h = hdr();
+    const int id = reinterpret_cast<const int*>(base + h.off_cost_id)[k];
+    return reinterpret_cast<const double*>(base + h.off_cost) + id * h.cost_stride;
+  }
+  __device__ __forceinline__ const ConSet& conset(int k) const {
+    const BlobHeader& h = hdr();
+    const int id = reinterpret_cast<const int*>(base + h.off_conset_id)[k];
+    return reinterpret_cast<const ConSet*>(base + h.off_conset)[id];
+  }
+  __device__ __forceinline__ float h(int k) const {
+    return reinterpret_cast<const float*>(base + hdr().off_h)[k];
+  }
+  __device__ __forceinline__ float t(int k) const {
+    return reinterpret_cast<const float*>(base + hdr().off_t)[k];
+  }
+  __device__ __forceinline__ const double* params() const {
+    return reinterpret_cast<const double*>(base + hdr().off_params);
+  }
+};
+
+// altro/common/solver_options.hpp:19-65 (numeric fields)
+struct DevOptions {
+  int max_iterations_total, max_iterations_outer, max_iterations_inner;
+  int bp_reg_fail_threshold, check_forwardpass_bounds, line_search_max_iterations, reset_duals;
+  int _pad;
+  double cost_tolerance, gradient_tolerance;
+  double bp_reg_increase_factor, bp_reg_initial, bp_reg_max, bp_reg_min;
+  double state_max, control_max;
+  double line_search_lower_bound, line_search_upper_bound, line_search_decrease_factor;
+  double constraint_tolerance, maximum_penalty, initial_penalty, penalty_scaling;
+};
+
+// Per-instance scalar state, SoA: sc[field][Bp], is[field][Bp].
+enum ScalarField : int {
+  S_REG = 0,       // rho_   (ilqr.hpp:802)
+  S_DREG,          // drho_  (ilqr.hpp:803)
+  S_DV0, S_DV1,    // deltaV_ (ilqr.hpp:804)
+  S_PENALTY,       // penalty rho of every constraint (uniform, constraint_values.hpp:202-207)
+  S_VIOL,          // GetMaxViolation() of the stored constraint values
+  S_COST,          // last Cost()/accepted J of the current trajectory  (costs_.sum())
+  S_INITIAL_COST,  // stats.initial_cost
+  S_COST_CUR,      // stats.cost.back()          (carry-forward, solver_stats.cpp:54-66)
+  S_COST_PREV,     // stats.cost.rbegin()[1]
+  S_DJ, S_GRAD, S_ALPHA, S_ZRATIO,   // stats.{cost_decrease,gradient,alpha,improvement_ratio}.back()
+  S_CSRC_ALPHA,    // Q8: < 0 -> stored constraint values come from Z; else alpha of the last
+                   //        evaluated (rejected) candidate
+  S_NUM
+};
+enum IntField : int {
+  I_STATUS = 0,    // iLQR status_
+  I_STATUS_AL,     // AugmentedLagrangianiLQR status_
+  I_ITERS_INNER, I_ITERS_OUTER, I_ITERS_TOTAL,
+  I_ZSEL,          // which of the two trajectory buffers currently is Z_ (the other is Zbar_)
+  I_NUM
+};
+
+struct SolverParams {
+  int B, T, N;
+  int n, m, pmax, use_al;
+  const char* blob;
+  int blob_bytes;
+  double* Z[2];   // [T][N+1][n+m][32]
+  double* KD;     // [T][N][m*n+m][32]      K (col-major m x n) then d
+  double* LAM;    // [T][N+1][pmax][32]     duals (nullptr when pmax == 0)
+  double* X0;     // [T][n][32]             initial states
+  double* EXP;    // [T][N+1][fexp][32]     materialised expansions (step-wise API only)
+  double* CTG;    // [T][N+1][n*n+n][32]    cost-to-go P, p (step-wise API only)
+  double* COSTS;  // [T][N+1][32]           costs_ vector (step-wise API only)
+  double* sc;     // [S_NUM][Bp]
+  int* is;        // [I_NUM][Bp]
+  DevOptions opt;
+};
+
+__host__ __device__ inline int exp_fields(int n, int m) {
+  return n * (n + m) + n * n + n * m + m * m + n + m;
+}
+
+}  // namespace altro_b200

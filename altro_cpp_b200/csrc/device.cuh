@@ -1,0 +1,595 @@
+// device.cuh — per-knot device functions of the AL-iLQR hot path, one problem instance per
+// thread, everything in registers, sizes known at compile time.
+//
+// These are NOT translations of the reference's Eigen code: the constraint terms are evaluated
+// structure-aware (a control bound touches one diagonal entry, a circle a 2x2 block) and no
+// dense p x (n+m) Jacobian is ever formed.  They are written so that every floating-point
+// sum keeps the association and term order of the reference — skipping
+// exact-zero terms does not change a sum — which keeps the fp64 results within ~1e-12 of the
+// CPU oracle and the discrete decisions (line search, Cholesky success) identical.
+#pragma once
+
+#include "common.cuh"
+
+namespace altro_b200 {
+
+#define ALTRO_UNROLL _Pragma("unroll")
+
+// C (r x c) = A (r x k) * B (k x c), column-major, inner index ascending.
+template <int r, int k, int c>
+__device__ __forceinline__ void matmul(const double* A, const double* B, double* C) {
+  ALTRO_UNROLL
+  for (int j = 0; j < c; ++j) {
+    ALTRO_UNROLL
+    for (int i = 0; i < r; ++i) {
+      double acc = A[i] * B[j * k];
+      ALTRO_UNROLL
+      for (int l = 1; l < k; ++l) acc += A[i + l * r] * B[l + j * k];
+      C[i + j * r] = acc;
+    }
+  }
+}
+// C (r x c) = A^T * B with A (k x r), B (k x c)
+template <int r, int k, int c>
+__device__ __forceinline__ void mattmul(const double* A, const double* B, double* C) {
+  ALTRO_UNROLL
+  for (int j = 0; j < c; ++j) {
+    ALTRO_UNROLL
+    for (int i = 0; i < r; ++i) {
+      double acc = A[i * k] * B[j * k];
+      ALTRO_UNROLL
+      for (int l = 1; l < k; ++l) acc += A[l + i * k] * B[l + j * k];
+      C[i + j * r] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Continuous models.  eval(): xdot = f(x,u);  jac(): dense A (n x n), B (n x m) col-major.
+// ------------------------------------------------------------------------------------------
+struct Unicycle {  // examples/unicycle.cpp:12-33
+  static constexpr int n = 3, m = 2;
+  static constexpr bool kDiscrete = false;
+  static __device__ __forceinline__ void eval(const double*, const double* x, const double* u,
+                                              double* xd) {
+    double s, c;
+    sincos(x[2], &s, &c);
+    xd[0] = u[0] * c;
+    xd[1] = u[0] * s;
+    xd[2] = u[1];
+  }
+  static __device__ __forceinline__ void jac(const double*, const double* x, const double* u,
+                                             double* A, double* B) {
+    double s, c;
+    sincos(x[2], &s, &c);
+    ALTRO_UNROLL
+    for (int i = 0; i < 9; ++i) A[i] = 0.0;
+    ALTRO_UNROLL
+    for (int i = 0; i < 6; ++i) B[i] = 0.0;
+    A[0 + 2 * 3] = -u[0] * s;
+    A[1 + 2 * 3] = u[0] * c;
+    B[0 + 0 * 3] = c;
+    B[1 + 0 * 3] = s;
+    B[2 + 1 * 3] = 1.0;
+  }
+};
+
+template <int dof>
+struct TripleIntegrator {  // examples/triple_integrator.cpp:9-33
+  static constexpr int n = 3 * dof, m = dof;
+  static constexpr bool kDiscrete = false;
+  static __device__ __forceinline__ void eval(const double*, const double* x, const double* u,
+                                              double* xd) {
+    ALTRO_UNROLL
+    for (int i = 0; i < dof; ++i) {
+      xd[i] = x[i + dof];
+      xd[i + dof] = x[i + 2 * dof];
+      xd[i + 2 * dof] = u[i];
+    }
+  }
+  static __device__ __forceinline__ void jac(const double*, const double*, const double*,
+                                             double* A, double* B) {
+    ALTRO_UNROLL
+    for (int i = 0; i < n * n; ++i) A[i] = 0.0;
+    ALTRO_UNROLL
+    for (int i = 0; i < n * m; ++i) B[i] = 0.0;
+    ALTRO_UNROLL
+    for (int i = 0; i < dof; ++i) {
+      A[i + (i + dof) * n] = 1.0;
+      A[(i + dof) + (i + 2 * dof) * n] = 1.0;
+      B[(i + 2 * dof) + i * n] = 1.0;
+    }
+  }
+};
+
+struct Cartpole {  // definition owned by this repo; oracle: altro_oracle.hpp ModelEvaluate
+  static constexpr int n = 4, m = 1;
+  static constexpr bool kDiscrete = false;
+  static __device__ __forceinline__ void eval(const double* P, const double* x, const double* u,
+                                              double* xd) {
+    const double mc = P[0], mp = P[1], l = P[2], g = P[3];
+    const double thd = x[3];
+    double s, c;
+    sincos(x[1], &s, &c);
+    const double den = mc + mp * s * s;
+    const double F = u[0];
+    xd[0] = x[2];
+    xd[1] = thd;
+    xd[2] = (F + mp * s * (l * thd * thd + g * c)) / den;
+    xd[3] = (-F * c - mp * l * thd * thd * c * s - (mc + mp) * g * s) / (l * den);
+  }
+  static __device__ __forceinline__ void jac(const double* P, const double* x, const double* u,
+                                             double* A, double* B) {
+    const double mc = P[0], mp = P[1], l = P[2], g = P[3];
+    const double thd = x[3];
+    double s, c;
+    sincos(x[1], &s, &c);
+    const double den = mc + mp * s * s;
+    const double F = u[0];
+    const double numx = F + mp * s * (l * thd * thd + g * c);
+    const double numt = -F * c - mp * l * thd * thd * c * s - (mc + mp) * g * s;
+    const double dden = 2.0 * mp * s * c;
+    const double dnumx = mp * c * (l * thd * thd + g * c) - mp * s * g * s;
+    const double dnumt = F * s - mp * l * thd * thd * (c * c - s * s) - (mc + mp) * g * c;
+    ALTRO_UNROLL
+    for (int i = 0; i < 16; ++i) A[i] = 0.0;
+    A[0 + 2 * 4] = 1.0;
+    A[1 + 3 * 4] = 1.0;
+    A[2 + 1 * 4] = (dnumx * den - numx * dden) / (den * den);
+    A[2 + 3 * 4] = (2.0 * mp * s * l * thd) / den;
+    A[3 + 1 * 4] = (dnumt * den - numt * dden) / (l * den * den);
+    A[3 + 3 * 4] = (-2.0 * mp * l * thd * c * s) / (l * den);
+    B[0] = 0.0;
+    B[1] = 0.0;
+    B[2] = 1.0 / den;
+    B[3] = -c / (l * den);
+  }
+};
+
+// RungeKutta4::Integrate, altro/problem/integration.hpp:124-131.  h is float, promoted (Q1).
+template <class M>
+__device__ __forceinline__ void rk4_step(const double* P, const double* x, const double* u,
+                                         float hf, double* xn) {
+  constexpr int n = M::n;
+  const double h = static_cast<double>(hf);
+  double k1[n], k2[n], k3[n], k4[n], xt[n];
+  M::eval(P, x, u, k1);
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * 0.5 * h;
+  M::eval(P, xt, u, k2);
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) xt[i] = x[i] + k2[i] * 0.5 * h;
+  M::eval(P, xt, u, k3);
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) xt[i] = x[i] + k3[i] * h;
+  M::eval(P, xt, u, k4);
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) xn[i] = x[i] + h * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]) / 6;
+}
+
+// RungeKutta4::Jacobian, altro/problem/integration.hpp:132-167.
+template <class M>
+__device__ __forceinline__ void rk4_jacobian(const double* P, const double* x, const double* u,
+                                             float hf, double* A, double* B) {
+  constexpr int n = M::n, m = M::m;
+  const double h = static_cast<double>(hf);
+  double k1[n], k2[n], k3[n], xt[n];
+  double As[n * n], Bs[n * m], dA[n * n], dB[n * m], T[n * n], T2[n * n], TB[n * m];
+  // stage 0
+  M::eval(P, x, u, k1);
+  M::jac(P, x, u, As, Bs);
+  ALTRO_UNROLL
+  for (int i = 0; i < n * n; ++i) { dA[i] = As[i] * h; A[i] = dA[i]; }
+  ALTRO_UNROLL
+  for (int i = 0; i < n * m; ++i) { dB[i] = Bs[i] * h; B[i] = dB[i]; }
+  // stage 1: x + 0.5*k1*h
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * 0.5 * h;
+  M::eval(P, xt, u, k2);
+  M::jac(P, xt, u, As, Bs);
+  ALTRO_UNROLL
+  for (int j = 0; j < n; ++j)
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) T[i + j * n] = (i == j ? 1.0 : 0.0) + 0.5 * dA[i + j * n];
+  matmul<n, n, n>(As, T, T2);
+  ALTRO_UNROLL
+  for (int i = 0; i < n * n; ++i) T[i] = 0.5 * As[i];
+  matmul<n, n, m>(T, dB, TB);
+  ALTRO_UNROLL
+  for (int i = 0; i < n * n; ++i) { dA[i] = T2[i] * h; A[i] = A[i] + 2 * dA[i]; }
+  ALTRO_UNROLL
+  for (int i = 0; i < n * m; ++i) { dB[i] = Bs[i] * h + TB[i] * h; B[i] = B[i] + 2 * dB[i]; }
+  // stage 2: x + 0.5*k2*h
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) xt[i] = x[i] + k2[i] * 0.5 * h;
+  M::eval(P, xt, u, k3);
+  M::jac(P, xt, u, As, Bs);
+  ALTRO_UNROLL
+  for (int j = 0; j < n; ++j)
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) T[i + j * n] = (i == j ? 1.0 : 0.0) + 0.5 * dA[i + j * n];
+  matmul<n, n, n>(As, T, T2);
+  ALTRO_UNROLL
+  for (int i = 0; i < n * n; ++i) T[i] = 0.5 * As[i];
+  matmul<n, n, m>(T, dB, TB);
+  ALTRO_UNROLL
+  for (int i = 0; i < n * n; ++i) { dA[i] = T2[i] * h; A[i] = A[i] + 2 * dA[i]; }
+  ALTRO_UNROLL
+  for (int i = 0; i < n * m; ++i) { dB[i] = Bs[i] * h + TB[i] * h; B[i] = B[i] + 2 * dB[i]; }
+  // stage 3: x + k3*h
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) xt[i] = x[i] + k3[i] * h;
+  M::jac(P, xt, u, As, Bs);
+  ALTRO_UNROLL
+  for (int j = 0; j < n; ++j)
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) T[i + j * n] = (i == j ? 1.0 : 0.0) + dA[i + j * n];
+  matmul<n, n, n>(As, T, T2);
+  matmul<n, n, m>(As, dB, TB);
+  ALTRO_UNROLL
+  for (int j = 0; j < n; ++j)
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) {
+      const int q = i + j * n;
+      A[q] = (i == j ? 1.0 : 0.0) + (A[q] + T2[q] * h) / 6;
+    }
+  ALTRO_UNROLL
+  for (int i = 0; i < n * m; ++i) B[i] = (B[i] + (Bs[i] * h + TB[i] * h)) / 6;
+}
+
+// ------------------------------------------------------------------------------------------
+// QuadraticCost (examples/quadratic_cost.cpp:8-28).  C = [Q (n*n), R (m*m), H (n*m), q, r, c].
+// ------------------------------------------------------------------------------------------
+template <int n, int m>
+__device__ __forceinline__ double quad_eval(const double* C, const double* x, const double* u) {
+  const double *Q = C, *R = C + n * n, *H = R + m * m, *q = H + n * m, *r = q + n;
+  double Qx[n], Hu[n], Ru[m];
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) {
+    double a = Q[i] * x[0];
+    ALTRO_UNROLL
+    for (int j = 1; j < n; ++j) a += Q[i + j * n] * x[j];
+    Qx[i] = a;
+    double b = H[i] * u[0];
+    ALTRO_UNROLL
+    for (int j = 1; j < m; ++j) b += H[i + j * n] * u[j];
+    Hu[i] = b;
+  }
+  ALTRO_UNROLL
+  for (int i = 0; i < m; ++i) {
+    double a = R[i] * u[0];
+    ALTRO_UNROLL
+    for (int j = 1; j < m; ++j) a += R[i + j * m] * u[j];
+    Ru[i] = a;
+  }
+  double xQx = x[0] * Qx[0], xHu = x[0] * Hu[0], qx = q[0] * x[0];
+  ALTRO_UNROLL
+  for (int i = 1; i < n; ++i) {
+    xQx += x[i] * Qx[i];
+    xHu += x[i] * Hu[i];
+    qx += q[i] * x[i];
+  }
+  double uRu = u[0] * Ru[0], ru = r[0] * u[0];
+  ALTRO_UNROLL
+  for (int i = 1; i < m; ++i) {
+    uRu += u[i] * Ru[i];
+    ru += r[i] * u[i];
+  }
+  return 0.5 * xQx + xHu + 0.5 * uRu + qx + ru + r[m];
+}
+
+template <int n, int m>
+__device__ __forceinline__ void quad_gradient(const double* C, const double* x, const double* u,
+                                              double* dx, double* du) {
+  const double *Q = C, *R = C + n * n, *H = R + m * m, *q = H + n * m, *r = q + n;
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) {
+    double a = Q[i] * x[0];
+    ALTRO_UNROLL
+    for (int j = 1; j < n; ++j) a += Q[i + j * n] * x[j];
+    double b = H[i] * u[0];
+    ALTRO_UNROLL
+    for (int j = 1; j < m; ++j) b += H[i + j * n] * u[j];
+    dx[i] = a + q[i] + b;
+  }
+  ALTRO_UNROLL
+  for (int i = 0; i < m; ++i) {
+    double a = R[i] * u[0];
+    ALTRO_UNROLL
+    for (int j = 1; j < m; ++j) a += R[i + j * m] * u[j];
+    double b = H[i * n] * x[0];
+    ALTRO_UNROLL
+    for (int j = 1; j < n; ++j) b += H[j + i * n] * x[j];
+    du[i] = a + r[i] + b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Augmented-Lagrangian terms of one knot.  lam points at the lane's dual column of the knot
+// (row r at lam[r*32]); rho is the scalar penalty (constraint_values.hpp:112, Q9).
+//
+// Reference: ConstraintValues::AugLag/AugLagGradient/AugLagHessian
+// (altro/constraints/constraint_values.hpp:111-177), cones constraint.hpp:28-122, summed per
+// constraint by ALCost (altro/augmented_lagrangian/al_cost.hpp:264-308).
+// ------------------------------------------------------------------------------------------
+
+// dynamic-index read of a small register array without local memory
+template <int len>
+__device__ __forceinline__ double pick(const double* v, int j) {
+  double r = v[0];
+  ALTRO_UNROLL
+  for (int i = 1; i < len; ++i) r = (j == i) ? v[i] : r;
+  return r;
+}
+template <int len>
+__device__ __forceinline__ void add_at(double* v, int j, double val) {
+  ALTRO_UNROLL
+  for (int i = 0; i < len; ++i) v[i] = (j == i) ? (v[i] + val) : v[i];
+}
+
+template <int n, int m>
+__device__ __forceinline__ double con_row_fast(const ConBlock& b, int i, const double* x,
+                                               const double* u) {
+  switch (b.kind) {
+    case kGoal:
+      return pick<n>(x, i) - b.a[i];
+    case kControlBound: {
+      const double uj = pick<m>(u, b.idx[i]);
+      return (i < b.nl) ? (b.a[i] - uj) : (uj - b.a[i]);
+    }
+    default: {
+      const double dx = pick<n>(x, b.xi) - b.a[i], dy = pick<n>(x, b.yi) - b.b[i];
+      return -(dx * dx + dy * dy - b.c[i] * b.c[i]);
+    }
+  }
+}
+
+// Adds the AL value of every constraint of a knot to J, one constraint at a time
+// (al_cost.hpp:266-272); also returns the max violation |c - Pi_K(c)|_inf
+// (constraint_values.hpp:216-221).
+template <int n, int m>
+__device__ __forceinline__ double al_value(const ConSet& cs, const double* x, const double* u,
+                                           const double* lam, double rho, double J,
+                                           double* viol) {
+  double v = 0.0;
+  for (int bi = 0; bi < cs.nblocks; ++bi) {
+    const ConBlock& b = cs.blk[bi];
+    double sa = 0.0, sb = 0.0;
+    for (int i = 0; i < b.p; ++i) {
+      const double c = con_row_fast<n, m>(b, i, x, u);
+      const double l = lam[(b.row0 + i) * kTile];
+      const double arg = l - rho * c;
+      const double lp = b.equality ? arg : fmin(0.0, arg);
+      sa += lp * lp;
+      sb += l * l;
+      v = fmax(v, b.equality ? fabs(c) : fabs(c - fmin(0.0, c)));
+    }
+    double Jb = sa - sb;
+    Jb = Jb / (2 * rho);
+    J += Jb;
+  }
+  if (viol) *viol = v;
+  return J;
+}
+
+// Adds the AL gradient and Gauss-Newton Hessian of every constraint of the knot to the cost
+// expansion (which already holds the QuadraticCost terms).
+template <int n, int m>
+__device__ __forceinline__ void al_expansion(const ConSet& cs, const double* x, const double* u,
+                                             const double* lam, double rho, double* lxx,
+                                             double* lxu, double* luu, double* lx, double* lu) {
+  (void)lxu;  // none of the device-capable constraints couples x and u
+  for (int bi = 0; bi < cs.nblocks; ++bi) {
+    const ConBlock& b = cs.blk[bi];
+    if (b.kind == kGoal) {
+      // J = [I | 0], identity dual cone: dx_i = -(lam_i - rho c_i), dxdx_ii = rho
+      ALTRO_UNROLL
+      for (int i = 0; i < n; ++i) {
+        if (i < b.p) {
+          const double c = x[i] - b.a[i];
+          const double lp = lam[(b.row0 + i) * kTile] - rho * c;
+          lx[i] += (-1.0) * lp;
+          lxx[i + i * n] += (rho * 1.0) * 1.0;
+        }
+      }
+    } else if (b.kind == kControlBound) {
+      // rows [0,nl): c = lb_j - u_j, J = -e_j ; rows [nl,nl+nu): c = u_j - ub_j, J = +e_j.
+      // Per control j the block contributes lower-row term first, then upper-row term.
+      double gdu[m], gduu[m];
+      bool hit[m];
+      ALTRO_UNROLL
+      for (int j = 0; j < m; ++j) { gdu[j] = 0.0; gduu[j] = 0.0; hit[j] = false; }
+      for (int i = 0; i < b.p; ++i) {
+        const int j = b.idx[i];
+        const double uj = pick<m>(u, j);
+        const bool lower = i < b.nl;
+        const double c = lower ? (b.a[i] - uj) : (uj - b.a[i]);
+        const double arg = lam[(b.row0 + i) * kTile] - rho * c;
+        const double lp = fmin(0.0, arg);
+        const double act = arg > 0 ? 0.0 : 1.0;      // constraint.hpp:112 (Q12)
+        const double jp = act * (lower ? -1.0 : 1.0);  // proj_jac * jac entry
+        const double g = (-jp) * lp;
+        const double hh = (rho * jp) * jp;
+        ALTRO_UNROLL
+        for (int jj = 0; jj < m; ++jj) {
+          if (jj == j) {
+            gdu[jj] = hit[jj] ? gdu[jj] + g : g;
+            gduu[jj] = hit[jj] ? gduu[jj] + hh : hh;
+            hit[jj] = true;
+          }
+        }
+      }
+      ALTRO_UNROLL
+      for (int j = 0; j < m; ++j) {
+        if (hit[j]) {
+          lu[j] += gdu[j];
+          luu[j + j * m] += gduu[j];
+        }
+      }
+    } else {
+      // circles: J(i, 0) = 2(cx - px), J(i, 1) = 2(cy - py) — columns 0 and 1 as the
+      // reference writes them (obstacle_constraints.hpp:117-118).
+      static_assert(n >= 2, "circle constraints need two position states");
+      const double px = pick<n>(x, b.xi), py = pick<n>(x, b.yi);
+      double g0 = 0.0, g1 = 0.0, h00 = 0.0, h01 = 0.0, h10 = 0.0, h11 = 0.0;
+      for (int i = 0; i < b.p; ++i) {
+        const double dx = px - b.a[i], dy = py - b.b[i];
+        const double c = -(dx * dx + dy * dy - b.c[i] * b.c[i]);
+        const double arg = lam[(b.row0 + i) * kTile] - rho * c;
+        const double lp = fmin(0.0, arg);
+        const double act = arg > 0 ? 0.0 : 1.0;
+        const double j0 = act * (2 * (b.a[i] - px));
+        const double j1 = act * (2 * (b.b[i] - py));
+        const double t0 = (-j0) * lp, t1 = (-j1) * lp;
+        const double r0 = rho * j0, r1 = rho * j1;
+        if (i == 0) {
+          g0 = t0; g1 = t1;
+          h00 = r0 * j0; h01 = r0 * j1; h10 = r1 * j0; h11 = r1 * j1;
+        } else {
+          g0 += t0; g1 += t1;
+          h00 += r0 * j0; h01 += r0 * j1; h10 += r1 * j0; h11 += r1 * j1;
+        }
+      }
+      lx[0] += g0;
+      lx[1] += g1;
+      lxx[0 + 0 * n] += h00;
+      lxx[0 + 1 * n] += h01;
+      lxx[1 + 0 * n] += h10;
+      lxx[1 + 1 * n] += h11;
+    }
+  }
+}
+
+// ALCost::Evaluate (al_cost.hpp:264-274) for knot k.
+template <int n, int m>
+__device__ __forceinline__ double knot_cost(const Desc& D, int k, const double* x,
+                                            const double* u, const double* lam, double rho,
+                                            double* viol) {
+  const double J = quad_eval<n, m>(D.cost(k), x, u);
+  return al_value<n, m>(D.conset(k), x, u, lam, rho, J, viol);
+}
+
+// Riccati step of the backward pass (knot_point_function_type.hpp:149-230) ----------------
+// In:  A,B, cost expansion, P,p of knot k+1, regularisation.  Out: K,d, P,p of knot k, dV.
+// Returns false when the Cholesky factorisation of Quu_reg hits a pivot <= 0 (Q19).
+template <int n, int m>
+__device__ __forceinline__ bool riccati_step(const double* A, const double* B, const double* lxx,
+                                             const double* lxu, const double* luu,
+                                             const double* lx, const double* lu, double* P,
+                                             double* p, double reg, double* K, double* d,
+                                             double* dV0, double* dV1) {
+  double Qxx[n * n], Qxu[n * m], Quu[m * m], Qx[n], Qu[m];
+  {
+    double AtP[n * n], BtP[m * n], T1[n * n], T2[n * m], T3[m * m], v[n], w[m];
+    mattmul<n, n, n>(A, P, AtP);          // A^T P
+    matmul<n, n, n>(AtP, A, T1);          // (A^T P) A
+    matmul<n, n, m>(AtP, B, T2);          // (A^T P) B
+    mattmul<m, n, n>(B, P, BtP);          // B^T P
+    matmul<m, n, m>(BtP, B, T3);          // (B^T P) B
+    mattmul<n, n, 1>(A, p, v);
+    mattmul<m, n, 1>(B, p, w);
+    ALTRO_UNROLL
+    for (int i = 0; i < n * n; ++i) Qxx[i] = lxx[i] + T1[i];
+    ALTRO_UNROLL
+    for (int i = 0; i < n * m; ++i) Qxu[i] = lxu[i] + T2[i];
+    ALTRO_UNROLL
+    for (int i = 0; i < m * m; ++i) Quu[i] = luu[i] + T3[i];
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) Qx[i] = lx[i] + v[i];
+    ALTRO_UNROLL
+    for (int i = 0; i < m; ++i) Qu[i] = lu[i] + w[i];
+  }
+  // RegularizeActionValue :175-186 + Eigen::LLT (lower, unblocked)
+  double L[m * m];
+  ALTRO_UNROLL
+  for (int j = 0; j < m; ++j)
+    ALTRO_UNROLL
+    for (int i = 0; i < m; ++i) L[i + j * m] = Quu[i + j * m] + (i == j ? 1.0 : 0.0) * reg;
+  bool ok = true;
+  ALTRO_UNROLL
+  for (int k = 0; k < m; ++k) {
+    double xk = L[k + k * m];
+    if (k > 0) {
+      double sq = 0.0;
+      ALTRO_UNROLL
+      for (int j = 0; j < k; ++j) sq += L[k + j * m] * L[k + j * m];
+      xk -= sq;
+    }
+    if (xk <= 0.0) ok = false;
+    xk = sqrt(xk);
+    L[k + k * m] = xk;
+    ALTRO_UNROLL
+    for (int i = k + 1; i < m; ++i) {
+      double a = L[i + k * m];
+      if (k > 0) {
+        double dot = 0.0;
+        ALTRO_UNROLL
+        for (int j = 0; j < k; ++j) dot += L[i + j * m] * L[k + j * m];
+        a -= dot;
+      }
+      L[i + k * m] = a / xk;
+    }
+  }
+  if (!ok) return false;
+  // K = -(L L^T)^-1 Qxu^T ; d = -(L L^T)^-1 Qu   (CalcGains :197-211)
+  ALTRO_UNROLL
+  for (int c = 0; c <= n; ++c) {
+    double bvec[m];
+    ALTRO_UNROLL
+    for (int i = 0; i < m; ++i) bvec[i] = (c < n) ? Qxu[(c < n ? c : 0) + i * n] : Qu[i];
+    ALTRO_UNROLL
+    for (int i = 0; i < m; ++i) {
+      double s = bvec[i];
+      ALTRO_UNROLL
+      for (int j = 0; j < i; ++j) s -= L[i + j * m] * bvec[j];
+      bvec[i] = s / L[i + i * m];
+    }
+    ALTRO_UNROLL
+    for (int i = m - 1; i >= 0; --i) {
+      double s = bvec[i];
+      ALTRO_UNROLL
+      for (int j = i + 1; j < m; ++j) s -= L[j + i * m] * bvec[j];
+      bvec[i] = s / L[i + i * m];
+    }
+    ALTRO_UNROLL
+    for (int i = 0; i < m; ++i) {
+      if (c < n) K[i + (c < n ? c : 0) * m] = bvec[i] * -1;
+      else d[i] = bvec[i] * -1;
+    }
+  }
+  // CalcCostToGo :220-230 — unregularised Q (Q3)
+  {
+    double KtQuu[n * m], v1[n], v2[n], v3[n], T1[n * n], T2[n * n], T3[n * n], Quud[m];
+    mattmul<n, m, m>(K, Quu, KtQuu);
+    matmul<n, m, 1>(KtQuu, d, v1);
+    mattmul<n, m, 1>(K, Qu, v2);
+    matmul<n, m, 1>(Qxu, d, v3);
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) p[i] = Qx[i] + v1[i] + v2[i] + v3[i];
+    matmul<n, m, n>(KtQuu, K, T1);
+    ALTRO_UNROLL
+    for (int j = 0; j < n; ++j)
+      ALTRO_UNROLL
+      for (int i = 0; i < n; ++i) {
+        double acc = K[i * m] * Qxu[j];
+        ALTRO_UNROLL
+        for (int l = 1; l < m; ++l) acc += K[l + i * m] * Qxu[j + l * n];
+        T2[i + j * n] = acc;
+      }
+    matmul<n, m, n>(Qxu, K, T3);
+    ALTRO_UNROLL
+    for (int i = 0; i < n * n; ++i) P[i] = Qxx[i] + T1[i] + T2[i] + T3[i];
+    double a = d[0] * Qu[0];
+    ALTRO_UNROLL
+    for (int i = 1; i < m; ++i) a += d[i] * Qu[i];
+    matmul<m, m, 1>(Quu, d, Quud);
+    double bq = d[0] * Quud[0];
+    ALTRO_UNROLL
+    for (int i = 1; i < m; ++i) bq += d[i] * Quud[i];
+    *dV0 += a;
+    *dV1 += 0.5 * bq;
+  }
+  return true;
+}
+
+}  // namespace altro_b200

@@ -102,10 +102,10 @@ class ProblemSpec:
     def build(self, lib, prefix: str):
         f = lambda name: getattr(lib, prefix + "problem_" + name)
         create = f("create")
-        create.restype = ctypes.c_void_p
-        create.argtypes = [ctypes.c_int] * 3
-        handle = ctypes.c_void_p(create(self.n, self.m, self.N))
-        if not handle:
+        create.restype = ctypes.c_int
+        create.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_void_p)]
+        handle = ctypes.c_void_p()
+        if create(self.n, self.m, self.N, ctypes.byref(handle)) != 0 or not handle:
             raise RuntimeError("problem_create failed")
         for call in self.calls:
             name, args = call[0], call[1:]

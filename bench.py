@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — AL-iLQR solves/sec (batched) on N B200s, with the backward-pass HBM roofline and
+the CPU baseline timed beside it.  Contract: see the task statement ("Measurement").
+
+A "step" is one pass of the hot path over one batch: B independent AL-iLQR solves of
+BASELINE.json config C2 (unicycle n=3, m=2, N=100, 3 obstacles + control bounds + goal;
+instance 0 nominal, the rest perturbed in x0 — SURVEY.md 8d), from the initial guess to the
+reference's termination, default SolverOptions.
+
+  value  = (B * n_gpus) / (max-over-ranks device time of one step), inputs resident in HBM
+  e2e    = same metric through the reference-facing host-buffer call altro_b200_solve_al_host
+           (pinned host x0 in, X/U/cost/viol/status/iters out, copies inside the timed region)
+  roofline = the materialised backward-pass kernel (k_backward_mat) timed live with CUDA events:
+           algorithmic bytes (SURVEY.md 8d contract, 37,696 B per instance per pass) / duration
+  cpu_baseline = the CPU oracle (a port of the reference's algorithm; the reference itself cannot
+           be built here — no Eigen) on all host cores over a bounded sample of the same batch
+
+`--impl reference` times that CPU path alone (rank 0 only) and prints the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from altro_cpp_b200 import problems as P  # noqa: E402
+
+METRIC = "AL-iLQR solves/sec (batched)"
+UNIT = "solves/s"
+
+
+def workload(name: str):
+    if name == "c2":
+        return P.unicycle_problem(P.K_THREE_OBSTACLES), P.UNICYCLE_X0_SCALE, 16384, \
+            "C2: unicycle n=3 m=2 N=100, 3 obstacles + control bounds + goal, AL-iLQR, default options"
+    if name == "c3":
+        return P.triple_integrator_problem(dof=2, N=50, add_constraints=True), P.TRIPLE_INTEGRATOR_X0_SCALE, \
+            8192, "C3: triple integrator n=6 m=2 N=50, goal + control bounds, AL-iLQR (8192 per GPU)"
+    if name == "c4":
+        return P.cartpole_problem(N=200), P.CARTPOLE_X0_SCALE, 32768, \
+            "C4: cartpole n=4 m=1 N=200, control bound, AL-iLQR"
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        clocks, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                clocks.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(clocks)) if clocks else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_leg(spec, X0, steps, warmup, sample, nthreads):
+    """Times the CPU oracle (port of the reference algorithm) on a bounded sample."""
+    from oracle import binding as ob
+    ob.build()
+    Xs = X0[:sample]
+    times = []
+    out = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = ob.solve_batch(spec, Xs, nthreads=nthreads, want_traj=False, want_gains=False)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sample / float(np.mean(times)), float(np.mean(times)), out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (default: the config's)")
+    ap.add_argument("--cpu-sample", type=int, default=2048)
+    ap.add_argument("--bp-iters", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    spec, scale, default_B, wl_name = workload(args.workload)
+    B = args.batch or default_B
+    ncores = os.cpu_count() or 1
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        X0 = P.perturbed_initial_states(spec, B, scale)
+        sample = min(args.cpu_sample, B)
+        W = max(1, min(args.warmup, 1))
+        val, dt, out = cpu_leg(spec, X0, args.steps, W, sample, ncores)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "batch_per_step": sample,
+                       "note": "CPU path of the reference algorithm (oracle port; the reference cannot be "
+                               "built here: Eigen absent), one independent solve per host thread"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
+                             "sample": f"first {sample} instances of the {B}-instance batch per step"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    import altro_cpp_b200 as pkg
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # Instances are generated once on rank 0 and scattered over NCCL (the only collective on the
+    # path: it shards trivially over the batch axis); results are gathered back.
+    n, m, N = spec.n, spec.m, spec.N
+    x0_dev = torch.empty((B, n), dtype=torch.float64, device=dev)
+    if rank == 0:
+        X0_all = P.perturbed_initial_states(spec, B * world, scale)
+        X0_all_dev = torch.from_numpy(X0_all).to(dev)
+    if distributed:
+        chunks = list(X0_all_dev.chunk(world)) if rank == 0 else None
+        dist.scatter(x0_dev, chunks, src=0)
+    else:
+        x0_dev.copy_(X0_all_dev)
+    X0_host = x0_dev.cpu().numpy()
+
+    stream = torch.cuda.Stream(device=dev)
+    solver = pkg.BatchSolver(spec, B, device=local_rank)
+    unom = spec.u0
+
+    def step():
+        solver.set_inputs_dev(x0_dev.data_ptr(), 0, unom, stream=stream)
+        solver.solve_al(stream=stream)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, args.warmup)):
+            step()
+        barrier()
+        l0 = solver.kernel_launches()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        launches = solver.kernel_launches() - l0
+        ms = e0.elapsed_time(e1) / args.steps
+    res = solver.results()
+
+    # ---- e2e: host buffers through altro_b200_solve_al_host (pinned memory)
+    pin_x0 = torch.from_numpy(X0_host).pin_memory()
+    outs = {k: torch.from_numpy(v).pin_memory() for k, v in solver.alloc_outputs(True).items()}
+    outs_np = {k: v.numpy() for k, v in outs.items()}
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            solver.solve_al_host(pin_x0.numpy(), None, True, stream=stream, out=outs_np)
+        barrier()
+        e2 = torch.cuda.Event(enable_timing=True)
+        e3 = torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        for _ in range(args.steps):
+            solver.solve_al_host(pin_x0.numpy(), None, True, stream=stream, out=outs_np)
+        e3.record(stream)
+        barrier()
+        ms_e2e = e2.elapsed_time(e3) / args.steps
+    h2d = B * n * 8
+    d2h = B * ((N + 1) * n + N * m) * 8 + B * (8 + 8 + 4 + 12)
+
+    # ---- roofline: the materialised backward-pass kernel, timed live
+    with torch.cuda.stream(stream):
+        solver.set_inputs_dev(x0_dev.data_ptr(), 0, unom, stream=stream)
+        solver.solve_setup(stream=stream)
+        solver.rollout(stream=stream)
+        solver.update_expansions(stream=stream)
+        for _ in range(3):
+            solver.backward_pass_stream_only(stream=stream)
+        barrier()
+        e4 = torch.cuda.Event(enable_timing=True)
+        e5 = torch.cuda.Event(enable_timing=True)
+        e4.record(stream)
+        for _ in range(args.bp_iters):
+            solver.backward_pass_stream_only(stream=stream)
+        e5.record(stream)
+        barrier()
+        ms_bp = e4.elapsed_time(e5) / args.bp_iters
+    bp_bytes = solver.backward_pass_bytes()
+    peak, peak_src = measured_peak()
+    achieved = bp_bytes / (ms_bp * 1e-3) / 1e9
+
+    # ---- reduce over ranks: max time, summed work
+    t = torch.tensor([ms, ms_e2e, ms_bp], dtype=torch.float64, device=dev)
+    stats = torch.tensor([float((res["status"] == 0).sum()), float(res["iters"][:, 2].sum()),
+                          float(res["iters"][:, 2].max())], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        smax = stats.clone()
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+        stats[2] = smax[2]
+        # gather per-instance results on rank 0 (cost, viol) — the output side of the scatter
+        cost_dev = torch.from_numpy(res["cost"]).to(dev)
+        gathered = [torch.empty_like(cost_dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(cost_dev, gathered, dst=0)
+    ms, ms_e2e, ms_bp_max = [float(v) for v in t.tolist()]
+    total = B * world
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        sample = min(args.cpu_sample, B)
+        val, dt, out = cpu_leg(spec, X0_host, 1, 0, sample, ncores)
+        same = float(np.mean(np.all(out["iters"] == res["iters"][:sample], axis=1)
+                             & (out["status"] == res["status"][:sample])))
+        cpu = {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
+               "sample": f"first {sample} instances of rank 0's batch, one pass ({dt:.1f} s)",
+               "same_status_and_iterations_as_gpu": same}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": wl_name, "batch_per_gpu": B, "global_batch": total,
+                       "parallelism": f"batch-sharded x{world} (no data-path collective)",
+                       "l2": f"working set {solver.device_bytes() / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)",
+                       "solved_fraction": float(stats[0].item() / total),
+                       "mean_ilqr_iterations": float(stats[1].item() / total),
+                       "max_ilqr_iterations": float(stats[2].item())},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_backward_mat (materialised backward pass, TMA-streamed)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "bytes_per_launch": bp_bytes, "ms_per_launch": ms_bp},
+            "solve_kernel": {"kernel": "k_solve (fused persistent AL-iLQR)",
+                             "backward_passes_per_step": float(stats[1].item()),
+                             "contract_GBps": float(stats[1].item()) * (bp_bytes / B) / (ms * 1e-3) / 1e9},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

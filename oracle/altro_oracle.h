@@ -42,7 +42,7 @@ typedef struct altro_oracle_options {
 void altro_oracle_default_options(altro_oracle_options* o);
 
 /* ---- problem description ---- */
-void* altro_oracle_problem_create(int n, int m, int N);
+int altro_oracle_problem_create(int n, int m, int N, void** out);
 void altro_oracle_problem_destroy(void* p);
 int altro_oracle_problem_set_model(void* p, int kind, const double* params, int nparams);
 int altro_oracle_problem_set_uniform_step(void* p, float h);

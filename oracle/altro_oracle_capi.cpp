@@ -226,7 +226,10 @@ void altro_oracle_default_options(altro_oracle_options* o) {
   o->penalty_scaling = d.penalty_scaling;
 }
 
-void* altro_oracle_problem_create(int n, int m, int N) { return new Problem(n, m, N); }
+int altro_oracle_problem_create(int n, int m, int N, void** out) {
+  *out = new Problem(n, m, N);
+  return 0;
+}
 void altro_oracle_problem_destroy(void* p) { delete static_cast<Problem*>(p); }
 
 int altro_oracle_problem_set_model(void* p, int kind, const double* params, int nparams) {

@@ -1,0 +1,363 @@
+"""GPU parity: the CUDA path (through the C ABI, include/altro_b200.h) against the CPU oracle
+on identical seeded inputs, plus the reference's golden values straight on the device and
+size-independent properties at BASELINE.json's full batch size.
+
+Tolerances: identical status and iteration counts per instance;
+X, U, K, d, cost to <= 1e-9 relative.  The oracle is compiled without FMA contraction, the
+device code with it, so bit equality is not expected; a handful of knife-edge instances may
+take a different discrete decision — the tests bound their fraction.
+"""
+import numpy as np
+import pytest
+
+from altro_cpp_b200 import problems as P
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (the product path has no CPU fallback)")
+    import altro_cpp_b200 as pkg
+    return pkg
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b)) / max(1.0, np.max(np.abs(b))))
+
+
+def close(a, b, tol=RTOL):
+    return rel_err(a, b) <= tol
+
+
+def oracle_stepper(oracle, spec, x0, al):
+    s = oracle.OracleSolver(spec, use_constraints=al)
+    s.set_initial_state(x0)
+    return s
+
+
+# ------------------------------------------------------------------------------------------
+# step-wise parity (public methods of iLQR<n,m>) on a ragged batch (B = 70: 2 full tiles + 6)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scenario,al", [(P.K_TURN90, False), (P.K_TURN90, True), (P.K_THREE_OBSTACLES, True)])
+def test_stepwise_unicycle(gpu, oracle, scenario, al):
+    spec = P.unicycle_problem(scenario)
+    B = 70
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, B, use_constraints=al)
+    s.set_inputs(X0)
+    if al and scenario == P.K_THREE_OBSTACLES:
+        s.set_penalty(10.0)
+    refs = []
+    for b in (0, 1, 37, 69):
+        r = oracle_stepper(oracle, spec, X0[b], al)
+        if al and scenario == P.K_THREE_OBSTACLES:
+            r.set_penalty(10.0)
+        refs.append((b, r))
+
+    s.solve_setup()
+    s.rollout()
+    J = s.cost()
+    for b, r in refs:
+        r.rollout()
+        assert close(J[b], r.cost(), 1e-12), "initial cost"
+    for it in range(3):
+        s.update_expansions()
+        ex = {k: s.expansion(k) for k in (0, 50, 99, 100)}
+        s.backward_pass()
+        K, d = s.gains()
+        P0, p0 = s.ctg(0)
+        sc = s.scalars()
+        for b, r in refs:
+            r.update_expansions()
+            for k, e in ex.items():
+                eo = r.expansion(k)
+                for name in ("lxx", "lxu", "luu", "lx", "lu"):
+                    assert close(e[name][b], eo[name], 1e-11), (it, k, name)
+                if k < 100:
+                    assert close(e["A"][b], eo["A"], 1e-12) and close(e["B"][b], eo["B"], 1e-12)
+            r.backward_pass()
+            Ko, do = r.gains()
+            assert close(K[b], Ko, 1e-9), f"K it={it}"
+            assert close(d[b], do, 1e-9), f"d it={it}"
+            Po, po = r.ctg(0)
+            assert close(P0[b], Po, 1e-9) and close(p0[b], po, 1e-9)
+            so = r.scalars()
+            assert close(sc["dV0"][b], so["deltaV"][0], 1e-9) and close(sc["dV1"][b], so["deltaV"][1], 1e-9)
+            assert sc["reg"][b] == so["rho"]
+        s.forward_pass()
+        Xg, Ug = s.trajectory()
+        sc = s.scalars()
+        res = s.results()
+        for b, r in refs:
+            r.forward_pass()
+            assert sc["alpha"][b] == r.stat("alpha")[-1], f"alpha it={it}"
+            Xo, Uo = r.trajectory()
+            assert close(Xg[b], Xo, 1e-10) and close(Ug[b], Uo, 1e-10)
+            assert close(res["cost"][b], r.stat("cost")[-1], 1e-11)
+    # dual / penalty update
+    if al:
+        s.update_duals()
+        s.update_penalties()
+        lam = {k: s.duals(k) for k in (0, 50, 100)}
+        for b, r in refs:
+            r.update_duals(); r.update_penalties()
+            for k, l in lam.items():
+                lo = r.duals(k)
+                assert close(l[b][: lo.size], lo, 1e-10), f"duals k={k}"
+            assert s.scalars()["penalty"][b] == r.max_penalty()
+
+
+def test_fused_backward_equals_materialised(gpu):
+    """sweep_backward (expansions in registers) and update_expansions + k_backward_mat (TMA
+    streamed records) are the same arithmetic."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    B = 96
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    out = []
+    for fused in (False, True):
+        s = gpu.BatchSolver(spec, B)
+        s.set_inputs(X0)
+        s.solve_setup(); s.rollout(); s.cost()
+        if fused:
+            s.backward_pass_fused()
+        else:
+            s.update_expansions(); s.backward_pass()
+        K, d = s.gains()
+        P0, p0 = s.ctg(0)
+        sc = s.scalars()
+        out.append((K, d, P0, p0, sc["dV0"], sc["dV1"]))
+    for a, b in zip(out[0], out[1]):
+        assert close(a, b, 1e-13)
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's golden values, straight on the device (instance 0 = nominal x0)
+# ------------------------------------------------------------------------------------------
+def test_golden_unicycle_ilqr(gpu):
+    # test/ilqr/unicycle_ilqr_test.cpp:90-100: 9 iterations, J = 0.0387016567, solved
+    spec = P.unicycle_problem(P.K_TURN90)
+    s = gpu.BatchSolver(spec, 32, use_constraints=False)
+    s.set_inputs(np.tile(spec.x0, (32, 1)))
+    s.solve_ilqr()
+    r = s.results()
+    assert np.all(r["iters"][:, 0] == 9) and np.all(r["status"] == 0)
+    assert np.all(np.abs(r["cost"] - 0.0387016567) < 1e-5)
+    assert np.all(r["cost"] == r["cost"][0])  # identical instances -> identical lanes
+
+
+def test_golden_auglag_full_solve(gpu):
+    # test/augmented_lagrangian/auglag_test.cpp:326-351: 14 total / 5 outer, cost 0.03893465058924039
+    spec = P.unicycle_problem(P.K_TURN90)
+    o = gpu.default_options()
+    o.constraint_tolerance = 1e-6
+    s = gpu.BatchSolver(spec, 40, options=o)
+    for _ in range(2):  # SolveTwice :353-380
+        s.set_inputs(np.tile(spec.x0, (40, 1)))
+        s.solve_al()
+    r = s.results()
+    assert np.all(r["iters"][:, 2] == 14) and np.all(r["iters"][:, 1] == 5) and np.all(r["status"] == 0)
+    assert np.all(np.abs(r["cost"] - 0.03893465058924039) / 0.03893465058924039 < 1e-10)
+    assert np.all(r["viol"] < 1e-6)
+
+
+def test_golden_three_obstacles(gpu):
+    # test/examples/example_unicycle_test.cpp:18-89
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    s = gpu.BatchSolver(spec, 32)
+    s.set_inputs(np.tile(spec.x0, (32, 1)))
+    s.rollout()
+    assert abs(s.cost()[0] - 141.9639680271223) < 1e-6
+    s.set_penalty(10.0)
+    assert abs(s.cost()[0] - 221.6032851439234) < 1e-6
+    s.solve_ilqr(); s.update_duals(); s.update_penalties()
+    lambdaN = np.array([0.43555910438329626, -0.5998598475208317, 0.0044282251970790935])
+    lam = s.duals(100)[0][:3]
+    assert np.linalg.norm(lam + lambdaN) <= 1e-6 * np.linalg.norm(lambdaN)
+    # full solve (Q10: Init() resets the penalty to 1)
+    s.set_inputs(np.tile(spec.x0, (32, 1)))
+    s.solve_al()
+    r = s.results()
+    assert np.all(r["status"] == 0) and np.all(r["viol"] < 1e-4)
+    assert tuple(r["iters"][0, 1:]) == (5, 50)
+    X, U = s.trajectory()
+    c = np.array([0.25, 0.5, 0.75]) * 3.0
+    for i in range(3):
+        dist = np.sqrt((X[0, :, 0] - c[i]) ** 2 + (X[0, :, 1] - c[i]) ** 2) - 0.425
+        assert dist.min() > -1e-3
+
+
+def test_golden_triple_integrator(gpu):
+    # test/ilqr/ilqr_test.cpp:304-336 (2 iterations, K0) and example_triple_integrator_test.cpp:39-70
+    spec = P.triple_integrator_problem(goal_only=True)
+    s = gpu.BatchSolver(spec, 32, use_constraints=False)
+    s.set_inputs(np.tile(spec.x0, (32, 1)))
+    s.solve_ilqr()
+    r = s.results()
+    assert np.all(r["status"] == 0) and np.all(r["iters"][:, 0] == 2)
+    K0 = np.array([[-63.9657, 0.0, -42.7673, 0.0, -11.5189, 0.0], [0.0, -63.9657, 0.0, -42.7673, 0.0, -11.5189]])
+    K, d = s.gains()
+    assert np.linalg.norm(K[0, 0] - K0) <= 1e-3 * np.linalg.norm(K0)
+    spec = P.triple_integrator_problem(add_constraints=True)
+    s = gpu.BatchSolver(spec, 32)
+    s.set_inputs(np.tile(spec.x0, (32, 1)))
+    s.solve_al()
+    r = s.results()
+    assert np.all(r["status"] == 0) and np.all(r["viol"] < 1e-4)
+    X, U = s.trajectory()
+    assert np.abs(X[0, 10] - spec.xf).max() < 1e-4
+    assert np.allclose(U[0, 0], [100.0, 200.0], rtol=1e-6) and np.allclose(U[0, 9], [100.0, 200.0], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------
+# whole solves against the oracle on seeded random batches
+# ------------------------------------------------------------------------------------------
+def compare_batch(gpu, oracle, spec, X0, al=True, options=None, max_mismatch_frac=0.02):
+    B = X0.shape[0]
+    og = options or gpu.default_options()
+    oo = oracle.default_options()
+    for name, _ in og._fields_:
+        if hasattr(oo, name):
+            setattr(oo, name, getattr(og, name))
+    s = gpu.BatchSolver(spec, B, use_constraints=al, options=og)
+    s.set_inputs(X0)
+    (s.solve_al if al else s.solve_ilqr)()
+    r = s.results()
+    Xg, Ug = s.trajectory()
+    Kg, dg = s.gains()
+    ref = oracle.solve_batch(spec, X0, options=oo, use_al=al, nthreads=8)
+    same = np.all(r["iters"] == ref["iters"], axis=1) & (r["status"] == ref["status"])
+    frac = 1.0 - same.mean()
+    assert frac <= max_mismatch_frac, f"{(~same).sum()} of {B} instances took a different discrete path"
+    idx = np.where(same)[0]
+    errs = dict(
+        X=max(rel_err(Xg[i], ref["X"][i]) for i in idx),
+        U=max(rel_err(Ug[i], ref["U"][i]) for i in idx),
+        K=max(rel_err(Kg[i], ref["K"][i]) for i in idx),
+        d=max(rel_err(dg[i], ref["d"][i]) for i in idx),
+        cost=max(rel_err(r["cost"][i], ref["cost"][i]) for i in idx),
+        viol=max(abs(r["viol"][i] - ref["viol"][i]) for i in idx),
+    )
+    return errs, frac, r, ref
+
+
+def test_solve_unicycle_turn90_ilqr(gpu, oracle):
+    spec = P.unicycle_problem(P.K_TURN90)
+    X0 = P.perturbed_initial_states(spec, 96, P.UNICYCLE_X0_SCALE)
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, al=False)
+    assert frac == 0.0
+    for k in ("X", "U", "K", "d", "cost"):
+        assert errs[k] <= RTOL, errs
+
+
+def test_solve_unicycle_turn90_al(gpu, oracle):
+    spec = P.unicycle_problem(P.K_TURN90)
+    X0 = P.perturbed_initial_states(spec, 96, P.UNICYCLE_X0_SCALE)
+    o = gpu.default_options()
+    o.constraint_tolerance = 1e-6
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, options=o)
+    for k in ("X", "U", "K", "d", "cost"):
+        assert errs[k] <= RTOL, errs
+    assert errs["viol"] <= 1e-12
+
+
+def test_solve_unicycle_three_obstacles_al(gpu, oracle):
+    # BASELINE config C2 at a batch the oracle finishes in seconds
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    X0 = P.perturbed_initial_states(spec, 256, P.UNICYCLE_X0_SCALE)
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0)
+    for k in ("X", "U", "cost"):
+        assert errs[k] <= 1e-8, errs
+    assert errs["K"] <= 1e-7 and errs["d"] <= 1e-7, errs
+    assert np.array_equal(r["status"] == 0, ref["status"] == 0)
+
+
+def test_solve_triple_integrator_al(gpu, oracle):
+    # BASELINE config C3 (N = 50, goal + bounds)
+    spec = P.triple_integrator_problem(dof=2, N=50, add_constraints=True)
+    X0 = P.perturbed_initial_states(spec, 96, P.TRIPLE_INTEGRATOR_X0_SCALE)
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0)
+    for k in ("X", "U", "cost"):
+        assert errs[k] <= 1e-8, errs
+
+
+def test_solve_cartpole_al(gpu, oracle):
+    # BASELINE config C4 (model not in the reference: parity is GPU vs oracle only)
+    spec = P.cartpole_problem(N=200)
+    X0 = P.perturbed_initial_states(spec, 64, P.CARTPOLE_X0_SCALE)
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, max_mismatch_frac=0.1)
+    for k in ("X", "U", "cost"):
+        assert errs[k] <= 1e-7, errs
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases and size-independent properties
+# ------------------------------------------------------------------------------------------
+def test_batch_of_one_and_ragged(gpu, oracle):
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    for B in (1, 33):
+        X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+        errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, max_mismatch_frac=0.0)
+        assert errs["X"] <= 1e-8
+
+
+def test_lane_placement_independence(gpu):
+    """1 GPU == 8 GPU analogue of the reference's nthreads-equivalence tests
+    (test/ilqr/ilqr_class_test.cpp:130-160): an instance's result does not depend on which
+    lane / tile / batch it is solved in — bit for bit."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    X0 = P.perturbed_initial_states(spec, 100, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, 100); s.set_inputs(X0); s.solve_al()
+    Xa, Ua = s.trajectory(); ra = s.results()
+    perm = np.random.default_rng(0).permutation(100)[:37]
+    s2 = gpu.BatchSolver(spec, 37); s2.set_inputs(X0[perm]); s2.solve_al()
+    Xb, Ub = s2.trajectory(); rb = s2.results()
+    assert np.array_equal(Xa[perm], Xb) and np.array_equal(Ua[perm], Ub)
+    assert np.array_equal(ra["cost"][perm], rb["cost"]) and np.array_equal(ra["iters"][perm], rb["iters"])
+
+
+def test_max_iterations_and_status_codes(gpu, oracle):
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    X0 = P.perturbed_initial_states(spec, 32, P.UNICYCLE_X0_SCALE)
+    o = gpu.default_options()
+    o.max_iterations_inner = 3
+    o.max_iterations_outer = 2
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, options=o, max_mismatch_frac=0.0)
+    assert set(np.unique(r["status"])) <= {0, 6, 7}
+    assert errs["X"] <= 1e-9
+
+
+def test_full_size_properties_c2(gpu):
+    """BASELINE config C2 at full size (B = 16384): size-independent properties.
+    (a) every solved instance satisfies its constraints to tolerance; (b) the returned
+    trajectory is dynamically feasible: an open-loop re-rollout of U reproduces X bit for
+    bit; (c) re-solving is deterministic; (d) instance 0 equals the golden nominal solve."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    B = 16384
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, B)
+    s.set_inputs(X0); s.solve_al()
+    r = s.results(); X, U = s.trajectory()
+    solved = r["status"] == 0
+    assert solved.mean() > 0.5  # ~30% of the perturbed instances stop at max_iterations_inner, as on the CPU
+    assert np.all(r["viol"][solved] < 1e-4)
+    assert tuple(r["iters"][0, 1:]) == (5, 50)
+    c = np.array([0.25, 0.5, 0.75]) * 3.0
+    for i in range(3):
+        dist = np.sqrt((X[solved, 1:100, 0] - c[i]) ** 2 + (X[solved, 1:100, 1] - c[i]) ** 2) - 0.425
+        assert dist.min() > -1e-3
+    assert np.all(U[solved, :, 0] <= 3 + 1e-3) and np.all(U[solved, :, 0] >= -1e-3)
+    assert np.all(np.abs(X[solved, 100] - spec.xf).max(axis=1) < 1e-3)
+    s2 = gpu.BatchSolver(spec, B, use_constraints=False)
+    s2.set_inputs(X0, U)
+    s2.rollout()
+    X2, _ = s2.trajectory()
+    assert np.array_equal(X2, X)
+    s.set_inputs(X0); s.solve_al()
+    Xr, Ur = s.trajectory()
+    assert np.array_equal(Xr, X) and np.array_equal(Ur, U)
