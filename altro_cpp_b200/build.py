@@ -33,12 +33,12 @@ def is_stale() -> bool:
     return False
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str = LIB, defines=()) -> str:
+    if out == LIB and not force and not is_stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if os.environ.get("ALTRO_B200_FMAD", "1") == "0":
         cmd.insert(1, "-fmad=false")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libaltro_b200.so")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

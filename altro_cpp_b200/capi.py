@@ -44,8 +44,8 @@ def lib():
     """Loads (building if stale) the CUDA library.  Fails loudly when it is missing."""
     global _lib
     if _lib is None:
-        path = _build.LIB
-        if _build.is_stale():
+        path = os.environ.get("ALTRO_B200_LIB") or _build.LIB  # override: A/B-testing build variants
+        if path == _build.LIB and _build.is_stale():
             path = _build.build()
         if not os.path.exists(path):
             raise SolverError("libaltro_b200.so is missing: run altro_cpp_b200/build.py (no CPU fallback)")

@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -138,53 +139,98 @@ int build_blob(const altro_b200_problem& p, bool use_constraints, std::vector<ch
 // Kernel dispatch per device-capable model
 // ------------------------------------------------------------------------------------------
 struct Ops {
-  void (*solve)(const SolverParams&, int mode, int smem, cudaStream_t);
-  void (*phase)(const SolverParams&, int phase, int smem, cudaStream_t);
-  void (*expansions)(const SolverParams&, int smem, cudaStream_t);
+  cudaError_t (*solve)(const SolverParams&, int mode, int budget, cudaStream_t);
+  cudaError_t (*phase)(const SolverParams&, int phase, cudaStream_t);
+  cudaError_t (*expansions)(const SolverParams&, cudaStream_t);
   cudaError_t (*backward_mat)(const SolverParams&, bool store_ctg, cudaStream_t);
 };
 
 constexpr int kBpStages = 4;
 
-template <class M>
+template <class M, int W>
+int solve_smem(const SolverParams& P) {
+  return ((P.blob_bytes + 15) / 16) * 16 + kSolveWarps * stage_doubles<M>(P.pmax, W) * sizeof(double);
+}
+
+template <class M, int W>
 Ops make_ops() {
   Ops o;
-  o.solve = [](const SolverParams& P, int mode, int smem, cudaStream_t st) {
-    k_solve<M><<<P.T, kTile, smem, st>>>(P, mode);
+  o.solve = [](const SolverParams& P, int mode, int budget, cudaStream_t st) -> cudaError_t {
+    const int smem = solve_smem<M, W>(P);
+    cudaError_t e = cudaFuncSetAttribute(k_solve<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k_solve<M, W><<<(P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st>>>(P, mode, budget);
+    return cudaGetLastError();
   };
-  o.phase = [](const SolverParams& P, int phase, int smem, cudaStream_t st) {
-    k_phase<M><<<P.T, kTile, smem, st>>>(P, phase);
+  o.phase = [](const SolverParams& P, int phase, cudaStream_t st) -> cudaError_t {
+    const int smem = solve_smem<M, W>(P);
+    cudaError_t e = cudaFuncSetAttribute(k_phase<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    k_phase<M, W><<<(P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st>>>(P, phase);
+    return cudaGetLastError();
   };
-  o.expansions = [](const SolverParams& P, int smem, cudaStream_t st) {
-    constexpr int kWarps = 4;
-    dim3 grid(P.T, (P.N + 1 + kWarps - 1) / kWarps);
-    k_update_expansions<M><<<grid, kWarps * kTile, smem, st>>>(P);
+  o.expansions = [](const SolverParams& P, cudaStream_t st) -> cudaError_t {
+    dim3 grid((P.B + 127) / 128, P.N + 1);
+    k_update_expansions<M, W><<<grid, 128, P.blob_bytes, st>>>(P);
+    return cudaGetLastError();
   };
   o.backward_mat = [](const SolverParams& P, bool store_ctg, cudaStream_t st) -> cudaError_t {
-    const int smem = kBpStages * Lane<M>::nexp * kTile * sizeof(double) + kBpStages * 8;
+    const int smem = kBpStages * Lane<M, W>::nexp * W * sizeof(double) + kBpStages * 8;
     cudaError_t e;
     if (store_ctg) {
-      e = cudaFuncSetAttribute(k_backward_mat<M, kBpStages, true>,
+      e = cudaFuncSetAttribute(k_backward_mat<M, W, kBpStages, true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
-      k_backward_mat<M, kBpStages, true><<<P.T, kTile, smem, st>>>(P);
+      k_backward_mat<M, W, kBpStages, true><<<P.T, kWarp, smem, st>>>(P);
     } else {
-      e = cudaFuncSetAttribute(k_backward_mat<M, kBpStages, false>,
+      e = cudaFuncSetAttribute(k_backward_mat<M, W, kBpStages, false>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
-      k_backward_mat<M, kBpStages, false><<<P.T, kTile, smem, st>>>(P);
+      k_backward_mat<M, W, kBpStages, false><<<P.T, kWarp, smem, st>>>(P);
     }
     return cudaGetLastError();
   };
   return o;
 }
 
-bool lookup_ops(int n, int m, int model, Ops* out) {
-  if (model == kUnicycle && n == 3 && m == 2) { if (out) *out = make_ops<Unicycle>(); return true; }
-  if (model == kTripleIntegrator && n == 6 && m == 2) { if (out) *out = make_ops<TripleIntegrator<2>>(); return true; }
-  if (model == kTripleIntegrator && n == 3 && m == 1) { if (out) *out = make_ops<TripleIntegrator<1>>(); return true; }
-  if (model == kCartpole && n == 4 && m == 1) { if (out) *out = make_ops<Cartpole>(); return true; }
+template <class M>
+bool ops_for_width(int W, Ops* out) {
+  if (W == 2) { if (out) *out = make_ops<M, 2>(); return true; }
+  if (W == 4) { if (out) *out = make_ops<M, 4>(); return true; }
+  if (W == 8) { if (out) *out = make_ops<M, 8>(); return true; }
+  if (W == 16) { if (out) *out = make_ops<M, 16>(); return true; }
+  if (W == 32) { if (out) *out = make_ops<M, 32>(); return true; }
   return false;
+}
+
+bool lookup_ops(int n, int m, int model, int W, Ops* out) {
+  if (model == kUnicycle && n == 3 && m == 2) return ops_for_width<Unicycle>(W, out);
+  if (model == kTripleIntegrator && n == 6 && m == 2) return ops_for_width<TripleIntegrator<2>>(W, out);
+  if (model == kTripleIntegrator && n == 3 && m == 1) return ops_for_width<TripleIntegrator<1>>(W, out);
+  if (model == kCartpole && n == 4 && m == 1) return ops_for_width<Cartpole>(W, out);
+  return false;
+}
+
+// Tile width: the serial sweeps are latency-bound, so a B200 wants >= ~14 warps per SM in flight.
+// Narrow tiles turn a small batch into more warps and free lane groups for the parallel line
+// search; a batch that already fills the machine uses full-width tiles.
+int choose_tile_width(int batch, int sm_count) {
+  if (const char* e = std::getenv("ALTRO_B200_TILE")) {
+    const int w = std::atoi(e);
+    if (w == 2 || w == 4 || w == 8 || w == 16 || w == 32) return w;
+  }
+  // widest tile that still yields ~14 warps per SM; never more warps than can be resident
+  // together (16 per SM at the solve kernel's register budget), never narrower than 2.
+  const long want = static_cast<long>(sm_count) * 14, resident = static_cast<long>(sm_count) * 16;
+  for (int w = 32; w >= 2; w /= 2) {
+    const long warps = (batch + w - 1) / w;
+    if (warps >= want || w == 2) {
+      int pick = w;
+      while (pick < 32 && (batch + pick - 1) / pick > resident) pick *= 2;
+      return pick;
+    }
+  }
+  return 8;
 }
 
 }  // namespace
@@ -193,7 +239,7 @@ bool lookup_ops(int n, int m, int model, Ops* out) {
 // Solver
 // ------------------------------------------------------------------------------------------
 struct altro_b200_solver {
-  int n, m, N, B, T, Bp, pmax, device, use_al;
+  int n, m, N, B, T, Bp, W, G, pmax, device, use_al;
   Ops ops;
   SolverParams P;
   char* d_blob = nullptr;
@@ -204,6 +250,15 @@ struct altro_b200_solver {
   int64_t launches = 0;
   std::vector<void*> allocs;
   bool inputs_set = false;
+  int model = 0, sm_count = 148;
+  // secondary workspaces: unfinished instances are re-packed into them between k_solve launches
+  struct Secondary {
+    SolverParams P;
+    Ops ops;
+    bool allocated = false;
+  } sec[2];
+  int* d_list = nullptr;
+  int* h_count = nullptr;  // pinned
 
   int alloc(void** p, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes);
@@ -222,7 +277,7 @@ struct altro_b200_solver {
     return 0;
   }
   int ensure_stepwise() {  // EXP / CTG / COSTS are only needed by the step-wise API
-    const size_t knots = static_cast<size_t>(T) * (N + 1) * kTile * sizeof(double);
+    const size_t knots = static_cast<size_t>(T) * (N + 1) * W * sizeof(double);
     if (!P.EXP) {
       int rc;
       if ((rc = alloc(reinterpret_cast<void**>(&P.EXP), knots * exp_fields(n, m)))) return rc;
@@ -298,7 +353,7 @@ int fill_int(altro_b200_solver* s, int field, int v, cudaStream_t st) {
 }
 
 // gather one tile-major array into instance-major staging, then to host
-int unpack_to(altro_b200_solver* s, const double* src0, const double* src1, int K, int F, int f0,
+int unpack_to(altro_b200_solver* s, const double* src0, int K, int F, int f0,
               int nf, int k0, int nk, double* dst, bool dst_is_host, bool by_zsel,
               cudaStream_t st) {
   const size_t bytes = static_cast<size_t>(s->B) * nk * nf * sizeof(double);
@@ -309,7 +364,7 @@ int unpack_to(altro_b200_solver* s, const double* src0, const double* src1, int 
     d = s->d_io;
   }
   dim3 grid((s->B + 127) / 128, nk);
-  k_unpack<<<grid, 128, 0, st>>>(s->P, src0, src1, K, F, f0, nf, k0, nk, d, by_zsel ? 1 : 0);
+  k_unpack<<<grid, 128, 0, st>>>(s->P, src0, K, F, f0, nf, k0, nk, d, by_zsel ? 1 : 0);
   int rc = check_launch(s, 1);
   if (rc) return rc;
   if (dst_is_host) {
@@ -353,7 +408,7 @@ void altro_b200_default_options(altro_b200_options* o) {  // solver_options.hpp:
   o->penalty_scaling = 10.0;
 }
 
-int altro_b200_is_supported(int n, int m, int model) { return lookup_ops(n, m, model, nullptr) ? 1 : 0; }
+int altro_b200_is_supported(int n, int m, int model) { return lookup_ops(n, m, model, 32, nullptr) ? 1 : 0; }
 
 // ---------------------------------------------------------------- problem
 int altro_b200_problem_create(int n, int m, int N, altro_b200_problem** out) {
@@ -482,8 +537,7 @@ int altro_b200_problem_set_initial_state(altro_b200_problem* p, const double* x0
 int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_constraints, int device,
                              altro_b200_solver** out) {
   if (!p || !out || batch <= 0) return fail(ALTRO_B200_ERR_ARG, "solver_create: bad argument");
-  Ops ops;
-  if (!lookup_ops(p->n, p->m, p->model, &ops))
+  if (!lookup_ops(p->n, p->m, p->model, 32, nullptr))
     return fail(ALTRO_B200_ERR_UNSUPPORTED, "no device instantiation for (n=" + std::to_string(p->n) + ", m=" +
                                                std::to_string(p->m) + ", model=" + std::to_string(p->model) + ")");
   int ndev = 0;
@@ -494,33 +548,44 @@ int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_con
   int rc = build_blob(*p, use_constraints != 0, &blob, &pmax);
   if (rc) return rc;
   DeviceGuard guard(device);
+  int sm_count = 148;
+  cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
   auto s = std::make_unique<altro_b200_solver>();
   s->n = p->n; s->m = p->m; s->N = p->N; s->B = batch;
-  s->T = (batch + kTile - 1) / kTile;
-  s->Bp = s->T * kTile;
+  s->W = choose_tile_width(batch, sm_count);
+  s->G = kWarp / s->W;
+  s->T = (batch + s->W - 1) / s->W;
+  s->Bp = s->T * s->W;
   s->pmax = pmax;
   s->device = device;
   s->use_al = use_constraints != 0;
-  s->ops = ops;
+  lookup_ops(p->n, p->m, p->model, s->W, &s->ops);
   std::memset(&s->P, 0, sizeof(s->P));
   SolverParams& P = s->P;
-  P.B = batch; P.T = s->T; P.N = p->N; P.n = p->n; P.m = p->m; P.pmax = pmax; P.use_al = s->use_al;
-  const size_t knots = static_cast<size_t>(s->T) * (p->N + 1) * kTile * sizeof(double);
+  P.B = batch; P.T = s->T; P.N = p->N; P.W = s->W; P.Bp = s->Bp;
+  P.n = p->n; P.m = p->m; P.pmax = pmax; P.use_al = s->use_al;
+  const size_t knots = static_cast<size_t>(s->T) * (p->N + 1) * s->W * sizeof(double);
   const int nz = p->n + p->m, nkd = p->m * p->n + p->m;
   if ((rc = s->alloc(reinterpret_cast<void**>(&s->d_blob), blob.size()))) return rc;
-  if ((rc = s->alloc(reinterpret_cast<void**>(&P.Z[0]), knots * nz))) return rc;
-  if ((rc = s->alloc(reinterpret_cast<void**>(&P.Z[1]), knots * nz))) return rc;
+  for (int zb = 0; zb < 1 + s->G; ++zb) {
+    if ((rc = s->alloc(reinterpret_cast<void**>(&P.Z[zb]), knots * nz))) return rc;
+    CU(cudaMemset(P.Z[zb], 0, knots * nz));
+  }
   if ((rc = s->alloc(reinterpret_cast<void**>(&P.KD), knots * nkd))) return rc;
   if (pmax > 0 && (rc = s->alloc(reinterpret_cast<void**>(&P.LAM), knots * pmax))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&P.X0), static_cast<size_t>(s->Bp) * p->n * sizeof(double)))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&P.sc), static_cast<size_t>(S_NUM) * s->Bp * sizeof(double)))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&P.is), static_cast<size_t>(I_NUM) * s->Bp * sizeof(int)))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&P.counters), 4 * sizeof(int)))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&s->d_list), static_cast<size_t>(s->Bp) * sizeof(int)))) return rc;
+  CU(cudaMemset(P.counters, 0, 4 * sizeof(int)));
+  CU(cudaHostAlloc(reinterpret_cast<void**>(&s->h_count), 4 * sizeof(int), cudaHostAllocDefault));
+  s->model = p->model;
+  s->sm_count = sm_count;
   CU(cudaMemcpy(s->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
   s->blob_bytes = static_cast<int>(blob.size());
   P.blob = s->d_blob;
   P.blob_bytes = s->blob_bytes;
-  CU(cudaMemset(P.Z[0], 0, knots * nz));
-  CU(cudaMemset(P.Z[1], 0, knots * nz));
   CU(cudaMemset(P.KD, 0, knots * nkd));  // KnotPointFunctions::Init :271-278
   if (pmax > 0) CU(cudaMemset(P.LAM, 0, knots * pmax));
   CU(cudaMemset(P.X0, 0, static_cast<size_t>(s->Bp) * p->n * sizeof(double)));
@@ -543,6 +608,7 @@ void altro_b200_solver_destroy(altro_b200_solver* s) {
   DeviceGuard guard(s->device);
   for (void* p : s->allocs) cudaFree(p);
   if (s->d_io) cudaFree(s->d_io);
+  if (s->h_count) cudaFreeHost(s->h_count);
   delete s;
 }
 
@@ -562,7 +628,7 @@ static int set_inputs_impl(altro_b200_solver* s, const double* x0_dev, const dou
     for (int i = 0; i < s->m; ++i) un.v[i] = u_nominal[i];
   }
   dim3 grid((s->Bp + 127) / 128, s->N + 1);
-  k_pack_inputs<<<grid, 128, 0, st>>>(s->P, x0_dev, U0_dev, un);
+  k_pack_inputs<<<grid, 128, 0, st>>>(s->P, x0_dev, U0_dev, un, 1 + s->G);
   s->inputs_set = true;
   return check_launch(s, 1);
 }
@@ -617,12 +683,101 @@ int altro_b200_solver_set_duals_host(altro_b200_solver* s, int k, const double* 
 }
 
 // ---------------------------------------------------------------- solves
+// Secondary workspace with room for `cap` instances at any tile width.
+static int ensure_secondary(altro_b200_solver* s, int which) {
+  altro_b200_solver::Secondary& w = s->sec[which];
+  if (w.allocated) return 0;
+  const int cap = s->Bp + kWarp;
+  const size_t knots = static_cast<size_t>(cap) * (s->N + 1) * sizeof(double);
+  const int nz = s->n + s->m, nkd = s->m * s->n + s->m;
+  std::memset(&w.P, 0, sizeof(w.P));
+  int rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.KD), knots * nkd))) return rc;
+  if (s->pmax > 0 && (rc = s->alloc(reinterpret_cast<void**>(&w.P.LAM), knots * s->pmax))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.X0), static_cast<size_t>(cap) * s->n * sizeof(double)))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.sc), static_cast<size_t>(S_NUM) * cap * sizeof(double)))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.is), static_cast<size_t>(I_NUM) * cap * sizeof(int)))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.counters), 4 * sizeof(int)))) return rc;
+  w.allocated = true;
+  return 0;
+}
+
+// trajectory buffers 0 .. nbuf-1 of a secondary workspace
+static int ensure_secondary_buffers(altro_b200_solver* s, int which, int nbuf) {
+  altro_b200_solver::Secondary& w = s->sec[which];
+  const int cap = s->Bp + kWarp;
+  const size_t bytes = static_cast<size_t>(cap) * (s->N + 1) * (s->n + s->m) * sizeof(double);
+  for (int zb = 0; zb < nbuf; ++zb) {
+    if (w.P.Z[zb]) continue;
+    int rc = s->alloc(reinterpret_cast<void**>(&w.P.Z[zb]), bytes);
+    if (rc) return rc;
+    cudaMemset(w.P.Z[zb], 0, bytes);
+  }
+  return 0;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
+
+// AugmentedLagrangianiLQR::Solve / iLQR::Solve for the whole batch.  Everything stays on the
+// device; the host only relaunches the resumable solve kernel and, when most instances are
+// done, re-packs the unfinished ones densely (their results are identical wherever they run).
 static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
   if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
   if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
   DeviceGuard guard(s->device);
-  s->ops.solve(s->P, mode, s->blob_bytes, st);
-  return check_launch(s, 1);
+  const int budget = std::max(1, env_int("ALTRO_B200_BUDGET", 32));
+  const int repack_pct = env_int("ALTRO_B200_REPACK_PCT", 60);  // 0 disables re-packing
+  int rc;
+  if ((rc = fill_int(s, I_PHASE, mode == 1 ? kPhAlInit : kPhSolveStart, st))) return rc;
+  k_iota<<<(s->Bp + 255) / 256, 256, 0, st>>>(s->P.is + static_cast<size_t>(I_ORIG) * s->Bp, s->Bp);
+  if ((rc = check_launch(s, 1))) return rc;
+  SolverParams* cur = &s->P;
+  Ops cur_ops = s->ops;
+  int cur_sec = -1;  // -1: primary
+  auto scatter_back = [&](SolverParams& from) -> int {
+    dim3 grid((from.B + 127) / 128, s->N + 2);
+    k_move_instances<<<grid, 128, 0, st>>>(from, s->P, nullptr, from.B, 1);
+    return check_launch(s, 1);
+  };
+  for (int launch = 0; launch < 100000; ++launch) {
+    cur->opt = s->P.opt;
+    CU(cudaMemsetAsync(cur->counters, 0, 4 * sizeof(int), st));
+    cudaError_t e = cur_ops.solve(*cur, mode, budget, st);
+    s->launches += 1;
+    if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("k_solve launch: ") + cudaGetErrorString(e));
+    CU(cudaMemcpyAsync(s->h_count, cur->counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const int unfinished = s->h_count[0];
+    if (unfinished == 0) break;
+    if (repack_pct > 0 && static_cast<long>(unfinished) * 100 <= static_cast<long>(cur->B) * repack_pct) {
+      const int nxt = (cur_sec == 0) ? 1 : 0;
+      if ((rc = ensure_secondary(s, nxt))) return rc;
+      altro_b200_solver::Secondary& w = s->sec[nxt];
+      k_list_unfinished<<<(cur->B + 255) / 256, 256, 0, st>>>(*cur, s->d_list);
+      if ((rc = check_launch(s, 1))) return rc;
+      SolverParams& Q = w.P;
+      Q.B = unfinished;
+      Q.W = choose_tile_width(unfinished, s->sm_count);
+      if ((rc = ensure_secondary_buffers(s, nxt, 1 + kWarp / Q.W))) return rc;
+      Q.T = (unfinished + Q.W - 1) / Q.W;
+      Q.Bp = Q.T * Q.W;
+      Q.N = s->N; Q.n = s->n; Q.m = s->m; Q.pmax = s->pmax; Q.use_al = s->use_al;
+      Q.blob = s->P.blob; Q.blob_bytes = s->P.blob_bytes;
+      lookup_ops(s->n, s->m, s->model, Q.W, &w.ops);
+      dim3 grid((unfinished + 127) / 128, s->N + 2);
+      k_move_instances<<<grid, 128, 0, st>>>(*cur, Q, s->d_list, unfinished, 0);
+      if ((rc = check_launch(s, 1))) return rc;
+      if (cur_sec >= 0 && (rc = scatter_back(*cur))) return rc;  // leave nothing behind in a secondary
+      cur = &Q;
+      cur_ops = w.ops;
+      cur_sec = nxt;
+    }
+  }
+  if (cur_sec >= 0 && (rc = scatter_back(*cur))) return rc;
+  return 0;
 }
 int altro_b200_solve_al(altro_b200_solver* s, void* stream) { return solve_impl(s, 1, S(stream)); }
 int altro_b200_solve_ilqr(altro_b200_solver* s, void* stream) { return solve_impl(s, 0, S(stream)); }
@@ -645,8 +800,10 @@ static int phase_impl(altro_b200_solver* s, int phase, cudaStream_t st) {
   DeviceGuard guard(s->device);
   int rc = s->ensure_stepwise();
   if (rc) return rc;
-  s->ops.phase(s->P, phase, s->blob_bytes, st);
-  return check_launch(s, 1);
+  cudaError_t e = s->ops.phase(s->P, phase, st);
+  s->launches += 1;
+  if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("k_phase launch: ") + cudaGetErrorString(e));
+  return 0;
 }
 int altro_b200_rollout(altro_b200_solver* s, void* stream) { return phase_impl(s, kPhaseRollout, S(stream)); }
 int altro_b200_cost(altro_b200_solver* s, void* stream) { return phase_impl(s, kPhaseCost, S(stream)); }
@@ -656,8 +813,10 @@ int altro_b200_update_expansions(altro_b200_solver* s, void* stream) {
   DeviceGuard guard(s->device);
   int rc = s->ensure_stepwise();
   if (rc) return rc;
-  s->ops.expansions(s->P, s->blob_bytes, S(stream));
-  return check_launch(s, 1);
+  cudaError_t e = s->ops.expansions(s->P, S(stream));
+  s->launches += 1;
+  if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("k_update_expansions launch: ") + cudaGetErrorString(e));
+  return 0;
 }
 int altro_b200_backward_pass(altro_b200_solver* s, void* stream) {
   if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
@@ -697,8 +856,8 @@ int altro_b200_get_trajectory_host(altro_b200_solver* s, double* X, double* U, v
   DeviceGuard guard(s->device);
   const int nz = s->n + s->m;
   int rc;
-  if (X && (rc = unpack_to(s, s->P.Z[0], s->P.Z[1], s->N + 1, nz, 0, s->n, 0, s->N + 1, X, true, true, S(stream)))) return rc;
-  if (U && (rc = unpack_to(s, s->P.Z[0], s->P.Z[1], s->N + 1, nz, s->n, s->m, 0, s->N, U, true, true, S(stream)))) return rc;
+  if (X && (rc = unpack_to(s, s->P.Z[0], s->N + 1, nz, 0, s->n, 0, s->N + 1, X, true, true, S(stream)))) return rc;
+  if (U && (rc = unpack_to(s, s->P.Z[0], s->N + 1, nz, s->n, s->m, 0, s->N, U, true, true, S(stream)))) return rc;
   return 0;
 }
 int altro_b200_get_trajectory_dev(altro_b200_solver* s, double* X, double* U, void* stream) {
@@ -706,8 +865,8 @@ int altro_b200_get_trajectory_dev(altro_b200_solver* s, double* X, double* U, vo
   DeviceGuard guard(s->device);
   const int nz = s->n + s->m;
   int rc;
-  if (X && (rc = unpack_to(s, s->P.Z[0], s->P.Z[1], s->N + 1, nz, 0, s->n, 0, s->N + 1, X, false, true, S(stream)))) return rc;
-  if (U && (rc = unpack_to(s, s->P.Z[0], s->P.Z[1], s->N + 1, nz, s->n, s->m, 0, s->N, U, false, true, S(stream)))) return rc;
+  if (X && (rc = unpack_to(s, s->P.Z[0], s->N + 1, nz, 0, s->n, 0, s->N + 1, X, false, true, S(stream)))) return rc;
+  if (U && (rc = unpack_to(s, s->P.Z[0], s->N + 1, nz, s->n, s->m, 0, s->N, U, false, true, S(stream)))) return rc;
   return 0;
 }
 int altro_b200_get_gains_host(altro_b200_solver* s, double* K, double* d, void* stream) {
@@ -715,8 +874,8 @@ int altro_b200_get_gains_host(altro_b200_solver* s, double* K, double* d, void* 
   DeviceGuard guard(s->device);
   const int nkd = s->m * s->n + s->m;
   int rc;
-  if (K && (rc = unpack_to(s, s->P.KD, nullptr, s->N, nkd, 0, s->m * s->n, 0, s->N, K, true, false, S(stream)))) return rc;
-  if (d && (rc = unpack_to(s, s->P.KD, nullptr, s->N, nkd, s->m * s->n, s->m, 0, s->N, d, true, false, S(stream)))) return rc;
+  if (K && (rc = unpack_to(s, s->P.KD, s->N, nkd, 0, s->m * s->n, 0, s->N, K, true, false, S(stream)))) return rc;
+  if (d && (rc = unpack_to(s, s->P.KD, s->N, nkd, s->m * s->n, s->m, 0, s->N, d, true, false, S(stream)))) return rc;
   return 0;
 }
 int altro_b200_get_ctg_host(altro_b200_solver* s, int k, double* Pm, double* p, void* stream) {
@@ -725,8 +884,8 @@ int altro_b200_get_ctg_host(altro_b200_solver* s, int k, double* Pm, double* p, 
   DeviceGuard guard(s->device);
   const int F = s->n * s->n + s->n;
   int rc;
-  if (Pm && (rc = unpack_to(s, s->P.CTG, nullptr, s->N + 1, F, 0, s->n * s->n, k, 1, Pm, true, false, S(stream)))) return rc;
-  if (p && (rc = unpack_to(s, s->P.CTG, nullptr, s->N + 1, F, s->n * s->n, s->n, k, 1, p, true, false, S(stream)))) return rc;
+  if (Pm && (rc = unpack_to(s, s->P.CTG, s->N + 1, F, 0, s->n * s->n, k, 1, Pm, true, false, S(stream)))) return rc;
+  if (p && (rc = unpack_to(s, s->P.CTG, s->N + 1, F, s->n * s->n, s->n, k, 1, p, true, false, S(stream)))) return rc;
   return 0;
 }
 int altro_b200_get_expansion_host(altro_b200_solver* s, int k, double* A, double* Bm, double* lxx, double* lxu,
@@ -740,7 +899,7 @@ int altro_b200_get_expansion_host(altro_b200_solver* s, int k, double* A, double
   int f0 = 0;
   for (int i = 0; i < 7; ++i) {
     if (outs[i]) {
-      int rc = unpack_to(s, s->P.EXP, nullptr, s->N + 1, F, f0, sizes[i], k, 1, outs[i], true, false, S(stream));
+      int rc = unpack_to(s, s->P.EXP, s->N + 1, F, f0, sizes[i], k, 1, outs[i], true, false, S(stream));
       if (rc) return rc;
     }
     f0 += sizes[i];
@@ -752,7 +911,7 @@ int altro_b200_get_duals_host(altro_b200_solver* s, int k, double* lambda, int* 
   DeviceGuard guard(s->device);
   if (p_out) *p_out = s->pmax;
   if (lambda && s->pmax > 0)
-    return unpack_to(s, s->P.LAM, nullptr, s->N + 1, s->pmax, 0, s->pmax, k, 1, lambda, true, false, S(stream));
+    return unpack_to(s, s->P.LAM, s->N + 1, s->pmax, 0, s->pmax, k, 1, lambda, true, false, S(stream));
   return 0;
 }
 int altro_b200_get_results_host(altro_b200_solver* s, double* cost, double* viol, int32_t* status,

@@ -1,14 +1,20 @@
 // common.cuh — problem descriptor, batch layout and per-instance state shared by the
 // kernels (kernels.cuh) and the C ABI (altro_b200.cu).
 //
-// Batch layout ("tile-major"): the batch is cut into tiles of 32 instances, one instance
-// per lane of a warp.  Every per-knot quantity is stored as
+// Batch layout ("tile-major"): the batch is cut into tiles of W instances (W = 2 .. 32,
+// chosen per solver from the batch size).  Every per-knot quantity is stored as
 //
-//     arr[tile][knot][field][lane]          (lane fastest, 32 doubles = 256 B per row)
+//     arr[tile][knot][field][i]          (i = instance within the tile, fastest; W*8 B per row)
 //
-// so a warp-wide access to one field of one knot is one fully coalesced 256 B request, and
-// the whole record of a (tile, knot) is one contiguous block (F*256 B) that a single
+// so an access to one field of one knot of a tile is one contiguous, sector-aligned row and
+// the whole record of a (tile, knot) is one contiguous block (F*W*8 B) that a single
 // cp.async.bulk (TMA 1-D bulk copy) can stage into shared memory.
+//
+// A warp always owns ONE tile.  Its 32 lanes are G = 32/W groups of W lanes: lane = a*W + i.
+// Lane group a = 0 carries the instances; groups a > 0 are the extra hands used where one
+// instance has parallel work of its own — the line search evaluates G step lengths of every
+// instance at once.  Small batches (B200: 148 SMs want >= ~2000 warps) use W = 8 so that the
+// latency-bound serial sweeps are spread over 4x more warps; huge batches use W = 32.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -16,7 +22,8 @@
 
 namespace altro_b200 {
 
-constexpr int kTile = 32;       // instances per tile (= warp size)
+constexpr int kWarp = 32;
+constexpr int kMaxZ = 17;       // trajectory buffers: Z_ plus up to G = 16 line-search candidates
 constexpr int kMaxDim = 32;     // max rows of one constraint block (and max n)
 constexpr int kMaxBlocks = 4;   // constraint blocks per knot (ALCost eq_ + ineq_ entries)
 constexpr unsigned kFull = 0xffffffffu;
@@ -131,30 +138,47 @@ enum ScalarField : int {
   S_DJ, S_GRAD, S_ALPHA, S_ZRATIO,   // stats.{cost_decrease,gradient,alpha,improvement_ratio}.back()
   S_CSRC_ALPHA,    // Q8: < 0 -> stored constraint values come from Z; else alpha of the last
                    //        evaluated (rejected) candidate
+  S_J0,            // costs_.sum() of the current Z_ (carried between launches of k_solve)
   S_NUM
 };
 enum IntField : int {
   I_STATUS = 0,    // iLQR status_
   I_STATUS_AL,     // AugmentedLagrangianiLQR status_
   I_ITERS_INNER, I_ITERS_OUTER, I_ITERS_TOTAL,
-  I_ZSEL,          // which of the two trajectory buffers currently is Z_ (the other is Zbar_)
+  I_ZSEL,          // which trajectory buffer currently is Z_ (the others hold line-search candidates)
+  I_PHASE,         // SolvePhase: where the instance is in its solve (k_solve is resumable)
+  I_ORIG,          // index of the instance in the solver's primary workspace (compaction)
   I_NUM
 };
 
+// k_solve is a resumable state machine: every instance advances by whole inner iterations
+// ("slots"); between launches the host may re-pack the unfinished instances densely.
+enum SolvePhase : int {
+  kPhAlInit = 0,      // AugmentedLagrangianiLQR::Init() pending
+  kPhSolveStart = 1,  // iLQR::Solve(): SolveSetup + Rollout + initial Cost pending
+  kPhInner = 2,       // next: UpdateExpansions/BackwardPass/ForwardPass of one inner iteration
+  kPhOuter = 3,       // iLQR solve ended: UpdateDuals / IsDone / UpdatePenalties pending
+  kPhDone = 4,        // terminated; final Cost() not reported yet
+  kPhReported = 5,    // everything written
+  kPhMoved = 6,       // continued in another workspace
+};
+
 struct SolverParams {
-  int B, T, N;
+  int B, T, N;    // instances, tiles, segments
+  int W, Bp;      // tile width, padded batch T*W
   int n, m, pmax, use_al;
   const char* blob;
   int blob_bytes;
-  double* Z[2];   // [T][N+1][n+m][32]
-  double* KD;     // [T][N][m*n+m][32]      K (col-major m x n) then d
-  double* LAM;    // [T][N+1][pmax][32]     duals (nullptr when pmax == 0)
-  double* X0;     // [T][n][32]             initial states
-  double* EXP;    // [T][N+1][fexp][32]     materialised expansions (step-wise API only)
-  double* CTG;    // [T][N+1][n*n+n][32]    cost-to-go P, p (step-wise API only)
-  double* COSTS;  // [T][N+1][32]           costs_ vector (step-wise API only)
+  double* Z[kMaxZ];  // [T][N+1][n+m][W]    trajectory buffers (1 + 32/W of them are allocated)
+  double* KD;     // [T][N][m*n+m][W]       K (col-major m x n) then d
+  double* LAM;    // [T][N+1][pmax][W]      duals (nullptr when pmax == 0)
+  double* X0;     // [T][n][W]              initial states
+  double* EXP;    // [T][N+1][fexp][W]      materialised expansions (step-wise API only)
+  double* CTG;    // [T][N+1][n*n+n][W]     cost-to-go P, p (step-wise API only)
+  double* COSTS;  // [T][N+1][W]            costs_ vector (step-wise API only)
   double* sc;     // [S_NUM][Bp]
   int* is;        // [I_NUM][Bp]
+  int* counters;  // [0] = instances not yet reported after the last k_solve launch
   DevOptions opt;
 };
 

@@ -347,7 +347,7 @@ __device__ __forceinline__ double con_row_fast(const ConBlock& b, int i, const d
 // Adds the AL value of every constraint of a knot to J, one constraint at a time
 // (al_cost.hpp:266-272); also returns the max violation |c - Pi_K(c)|_inf
 // (constraint_values.hpp:216-221).
-template <int n, int m>
+template <int n, int m, int LS>
 __device__ __forceinline__ double al_value(const ConSet& cs, const double* x, const double* u,
                                            const double* lam, double rho, double J,
                                            double* viol) {
@@ -357,7 +357,7 @@ __device__ __forceinline__ double al_value(const ConSet& cs, const double* x, co
     double sa = 0.0, sb = 0.0;
     for (int i = 0; i < b.p; ++i) {
       const double c = con_row_fast<n, m>(b, i, x, u);
-      const double l = lam[(b.row0 + i) * kTile];
+      const double l = lam[(b.row0 + i) * LS];
       const double arg = l - rho * c;
       const double lp = b.equality ? arg : fmin(0.0, arg);
       sa += lp * lp;
@@ -374,7 +374,7 @@ __device__ __forceinline__ double al_value(const ConSet& cs, const double* x, co
 
 // Adds the AL gradient and Gauss-Newton Hessian of every constraint of the knot to the cost
 // expansion (which already holds the QuadraticCost terms).
-template <int n, int m>
+template <int n, int m, int LS>
 __device__ __forceinline__ void al_expansion(const ConSet& cs, const double* x, const double* u,
                                              const double* lam, double rho, double* lxx,
                                              double* lxu, double* luu, double* lx, double* lu) {
@@ -387,7 +387,7 @@ __device__ __forceinline__ void al_expansion(const ConSet& cs, const double* x, 
       for (int i = 0; i < n; ++i) {
         if (i < b.p) {
           const double c = x[i] - b.a[i];
-          const double lp = lam[(b.row0 + i) * kTile] - rho * c;
+          const double lp = lam[(b.row0 + i) * LS] - rho * c;
           lx[i] += (-1.0) * lp;
           lxx[i + i * n] += (rho * 1.0) * 1.0;
         }
@@ -404,7 +404,7 @@ __device__ __forceinline__ void al_expansion(const ConSet& cs, const double* x, 
         const double uj = pick<m>(u, j);
         const bool lower = i < b.nl;
         const double c = lower ? (b.a[i] - uj) : (uj - b.a[i]);
-        const double arg = lam[(b.row0 + i) * kTile] - rho * c;
+        const double arg = lam[(b.row0 + i) * LS] - rho * c;
         const double lp = fmin(0.0, arg);
         const double act = arg > 0 ? 0.0 : 1.0;      // constraint.hpp:112 (Q12)
         const double jp = act * (lower ? -1.0 : 1.0);  // proj_jac * jac entry
@@ -435,7 +435,7 @@ __device__ __forceinline__ void al_expansion(const ConSet& cs, const double* x, 
       for (int i = 0; i < b.p; ++i) {
         const double dx = px - b.a[i], dy = py - b.b[i];
         const double c = -(dx * dx + dy * dy - b.c[i] * b.c[i]);
-        const double arg = lam[(b.row0 + i) * kTile] - rho * c;
+        const double arg = lam[(b.row0 + i) * LS] - rho * c;
         const double lp = fmin(0.0, arg);
         const double act = arg > 0 ? 0.0 : 1.0;
         const double j0 = act * (2 * (b.a[i] - px));
@@ -461,12 +461,12 @@ __device__ __forceinline__ void al_expansion(const ConSet& cs, const double* x, 
 }
 
 // ALCost::Evaluate (al_cost.hpp:264-274) for knot k.
-template <int n, int m>
+template <int n, int m, int LS>
 __device__ __forceinline__ double knot_cost(const Desc& D, int k, const double* x,
                                             const double* u, const double* lam, double rho,
                                             double* viol) {
   const double J = quad_eval<n, m>(D.cost(k), x, u);
-  return al_value<n, m>(D.conset(k), x, u, lam, rho, J, viol);
+  return al_value<n, m, LS>(D.conset(k), x, u, lam, rho, J, viol);
 }
 
 // Riccati step of the backward pass (knot_point_function_type.hpp:149-230) ----------------

@@ -895,9 +895,11 @@ struct iLQR {
       costfun[k].Gradient(x(k), u(k), f.lx, f.lu);
       costfun[k].Hessian(x(k), u(k), f.lxx, f.lxu, f.luu);
       // CalcDynamicsExpansion :121-128 (knot N holds IdentityDynamics, problem.hpp:161-164)
+      std::memset(f.jac, 0, sizeof(f.jac));
       if (k < N) {
-        std::memset(f.jac, 0, sizeof(f.jac));
         DiscreteJacobian<n, m>(*prob, x(k), u(k), prob->t[k], prob->h[k], f.jac);
+      } else {  // IdentityDynamics::Jacobian, problem.hpp:40-43: jac.setIdentity() on n x (n+m)
+        for (int i = 0; i < n; ++i) f.jac[i + i * n] = 1.0;
       }
       costs[k] = costfun[k].Evaluate(x(k), u(k));
     }
