@@ -157,7 +157,7 @@ def main():
             return
         X0 = P.perturbed_initial_states(spec, B, scale)
         sample = min(args.cpu_sample, B)
-        W = max(1, min(args.warmup, 1))
+        W = max(0, args.warmup)
         val, dt, out = cpu_leg(spec, X0, args.steps, W, sample, ncores)
         line = {
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
@@ -189,16 +189,16 @@ def main():
 
     # Instances are generated once on rank 0 and scattered over NCCL (the only collective on the
     # path: it shards trivially over the batch axis); results are gathered back.
+    from altro_cpp_b200.sharding import gather_rows, scatter_rows
     n, m, N = spec.n, spec.m, spec.N
-    x0_dev = torch.empty((B, n), dtype=torch.float64, device=dev)
+    total = B * world
+    X0_all_dev = None
     if rank == 0:
-        X0_all = P.perturbed_initial_states(spec, B * world, scale)
-        X0_all_dev = torch.from_numpy(X0_all).to(dev)
+        X0_all_dev = torch.from_numpy(P.perturbed_initial_states(spec, total, scale)).to(dev)
     if distributed:
-        chunks = list(X0_all_dev.chunk(world)) if rank == 0 else None
-        dist.scatter(x0_dev, chunks, src=0)
+        x0_dev = scatter_rows(X0_all_dev, total, (n,), torch.float64, dev)
     else:
-        x0_dev.copy_(X0_all_dev)
+        x0_dev = X0_all_dev
     X0_host = x0_dev.cpu().numpy()
 
     stream = torch.cuda.Stream(device=dev)
@@ -284,12 +284,10 @@ def main():
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
         dist.all_reduce(smax, op=dist.ReduceOp.MAX)
         stats[2] = smax[2]
-        # gather per-instance results on rank 0 (cost, viol) — the output side of the scatter
-        cost_dev = torch.from_numpy(res["cost"]).to(dev)
-        gathered = [torch.empty_like(cost_dev) for _ in range(world)] if rank == 0 else None
-        dist.gather(cost_dev, gathered, dst=0)
+        # gather per-instance results on rank 0 — the output side of the scatter
+        cost_all = gather_rows(torch.from_numpy(res["cost"]).to(dev).reshape(-1, 1), total)
+        assert rank != 0 or cost_all.shape[0] == total
     ms, ms_e2e, ms_bp_max = [float(v) for v in t.tolist()]
-    total = B * world
 
     cpu = None
     if rank == 0 and not args.no_cpu:

@@ -81,8 +81,9 @@ if __name__ == "__main__":
     if what in ("all", "diffs"): diffs()
     if what in ("all", "timings"): timings()
     if what == "ncu_solve":
+        # one k_solve launch of the C2 batch: AL init + rollout + 3 inner iterations of every instance
         spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
-        B = 4736
+        B = 16384
         X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
         o = pkg.default_options(); o.max_iterations_inner = 3; o.max_iterations_outer = 1
         s = pkg.BatchSolver(spec, B, options=o); s.set_inputs(X0); s.solve_al(); torch.cuda.synchronize()
