@@ -175,18 +175,19 @@ Ops make_ops() {
     return cudaGetLastError();
   };
   o.backward_mat = [](const SolverParams& P, bool store_ctg, cudaStream_t st) -> cudaError_t {
-    const int smem = kBpStages * Lane<M, W>::nexp * W * sizeof(double) + kBpStages * 8;
+    const int smem = kBpStages * Lane<M, W>::nexp * kWarp * sizeof(double) + kBpStages * 8;
+    const int grid = (P.T + kWarp / W - 1) / (kWarp / W);
     cudaError_t e;
     if (store_ctg) {
       e = cudaFuncSetAttribute(k_backward_mat<M, W, kBpStages, true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
-      k_backward_mat<M, W, kBpStages, true><<<P.T, kWarp, smem, st>>>(P);
+      k_backward_mat<M, W, kBpStages, true><<<grid, kWarp, smem, st>>>(P);
     } else {
       e = cudaFuncSetAttribute(k_backward_mat<M, W, kBpStages, false>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
-      k_backward_mat<M, W, kBpStages, false><<<P.T, kWarp, smem, st>>>(P);
+      k_backward_mat<M, W, kBpStages, false><<<grid, kWarp, smem, st>>>(P);
     }
     return cudaGetLastError();
   };

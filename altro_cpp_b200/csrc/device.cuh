@@ -15,6 +15,16 @@ namespace altro_b200 {
 
 #define ALTRO_UNROLL _Pragma("unroll")
 
+// x / y given ry = RN(1/y): one multiply and two FMAs instead of the ~12-instruction division
+// sequence.  With a correctly rounded reciprocal the residual correction returns the correctly
+// rounded quotient (Markstein), i.e. the same bits as `x / y`, so the reference's divisions
+// (`/ 6` in RK4, the triangular solves of LLT, `/ (2 rho)`) keep their results.
+__device__ __forceinline__ double div_by(double x, double y, double ry) {
+  const double q = x * ry;
+  const double r = fma(-q, y, x);
+  return fma(r, ry, q);
+}
+
 // C (r x c) = A (r x k) * B (k x c), column-major, inner index ascending.
 template <int r, int k, int c>
 __device__ __forceinline__ void matmul(const double* A, const double* B, double* C) {
@@ -164,7 +174,9 @@ __device__ __forceinline__ void rk4_step(const double* P, const double* x, const
   for (int i = 0; i < n; ++i) xt[i] = x[i] + k3[i] * h;
   M::eval(P, xt, u, k4);
   ALTRO_UNROLL
-  for (int i = 0; i < n; ++i) xn[i] = x[i] + h * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]) / 6;
+  const double r6 = 1.0 / 6.0;
+  ALTRO_UNROLL
+  for (int i = 0; i < n; ++i) xn[i] = x[i] + div_by(h * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]), 6.0, r6);
 }
 
 // RungeKutta4::Jacobian, altro/problem/integration.hpp:132-167.
@@ -231,10 +243,10 @@ __device__ __forceinline__ void rk4_jacobian(const double* P, const double* x, c
     ALTRO_UNROLL
     for (int i = 0; i < n; ++i) {
       const int q = i + j * n;
-      A[q] = (i == j ? 1.0 : 0.0) + (A[q] + T2[q] * h) / 6;
+      A[q] = (i == j ? 1.0 : 0.0) + div_by(A[q] + T2[q] * h, 6.0, 1.0 / 6.0);
     }
   ALTRO_UNROLL
-  for (int i = 0; i < n * m; ++i) B[i] = (B[i] + (Bs[i] * h + TB[i] * h)) / 6;
+  for (int i = 0; i < n * m; ++i) B[i] = div_by(B[i] + (Bs[i] * h + TB[i] * h), 6.0, 1.0 / 6.0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -352,6 +364,8 @@ __device__ __forceinline__ double al_value(const ConSet& cs, const double* x, co
                                            const double* lam, double rho, double J,
                                            double* viol) {
   double v = 0.0;
+  const double two_rho = 2 * rho;
+  const double r_two_rho = (cs.nblocks > 0) ? 1.0 / two_rho : 0.0;
   for (int bi = 0; bi < cs.nblocks; ++bi) {
     const ConBlock& b = cs.blk[bi];
     double sa = 0.0, sb = 0.0;
@@ -365,7 +379,7 @@ __device__ __forceinline__ double al_value(const ConSet& cs, const double* x, co
       v = fmax(v, b.equality ? fabs(c) : fabs(c - fmin(0.0, c)));
     }
     double Jb = sa - sb;
-    Jb = Jb / (2 * rho);
+    Jb = div_by(Jb, two_rho, r_two_rho);
     J += Jb;
   }
   if (viol) *viol = v;
@@ -500,7 +514,7 @@ __device__ __forceinline__ bool riccati_step(const double* A, const double* B, c
     for (int i = 0; i < m; ++i) Qu[i] = lu[i] + w[i];
   }
   // RegularizeActionValue :175-186 + Eigen::LLT (lower, unblocked)
-  double L[m * m];
+  double L[m * m], rL[m];
   ALTRO_UNROLL
   for (int j = 0; j < m; ++j)
     ALTRO_UNROLL
@@ -518,6 +532,7 @@ __device__ __forceinline__ bool riccati_step(const double* A, const double* B, c
     if (xk <= 0.0) ok = false;
     xk = sqrt(xk);
     L[k + k * m] = xk;
+    rL[k] = 1.0 / xk;
     ALTRO_UNROLL
     for (int i = k + 1; i < m; ++i) {
       double a = L[i + k * m];
@@ -527,7 +542,7 @@ __device__ __forceinline__ bool riccati_step(const double* A, const double* B, c
         for (int j = 0; j < k; ++j) dot += L[i + j * m] * L[k + j * m];
         a -= dot;
       }
-      L[i + k * m] = a / xk;
+      L[i + k * m] = div_by(a, xk, rL[k]);
     }
   }
   if (!ok) return false;
@@ -542,14 +557,14 @@ __device__ __forceinline__ bool riccati_step(const double* A, const double* B, c
       double s = bvec[i];
       ALTRO_UNROLL
       for (int j = 0; j < i; ++j) s -= L[i + j * m] * bvec[j];
-      bvec[i] = s / L[i + i * m];
+      bvec[i] = div_by(s, L[i + i * m], rL[i]);
     }
     ALTRO_UNROLL
     for (int i = m - 1; i >= 0; --i) {
       double s = bvec[i];
       ALTRO_UNROLL
       for (int j = i + 1; j < m; ++j) s -= L[j + i * m] * bvec[j];
-      bvec[i] = s / L[i + i * m];
+      bvec[i] = div_by(s, L[i + i * m], rL[i]);
     }
     ALTRO_UNROLL
     for (int i = 0; i < m; ++i) {

@@ -1095,30 +1095,39 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 }
 
 // Backward pass over materialised expansions: the kernel BASELINE.json's "backward-pass HBM
-// GB/s" is quoted on.  One warp per tile (lanes >= W idle: with small batches the recursion is
-// latency-bound and more, narrower warps keep more records in flight); the (tile, knot) records
-// (nexp*W*8 B each, contiguous) are streamed N-1 .. 0 through a kStages-deep shared-memory ring
-// by TMA bulk copies issued by lane 0 and tracked with mbarriers; every lane then reads its own
-// column (conflict-free) and runs the Riccati step in registers.  Writes K, d (and P, p when
-// kStoreCtg).
+// GB/s" is quoted on.  Every lane is one instance: a warp owns 32/W consecutive tiles (lane =
+// t*W + i).  The (tile, knot) records (nexp*W*8 B each, contiguous) are streamed N-1 .. 0 through
+// a kStages-deep shared-memory ring by TMA bulk copies (one per tile per knot) issued by lane 0
+// and tracked with mbarriers; every lane then reads its own column (conflict-free) and runs the
+// Riccati step in registers.  Writes K, d (and P, p when kStoreCtg).
 template <class M, int W, int kStages, bool kStoreCtg>
 __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
-  constexpr int n = M::n, m = M::m, nexp = Lane<M, W>::nexp;
-  constexpr uint32_t kRecBytes = nexp * W * sizeof(double);
+  constexpr int n = M::n, m = M::m, nexp = Lane<M, W>::nexp, TPW = kWarp / W;
+  constexpr uint32_t kRecBytes = nexp * W * sizeof(double);       // one tile's record
+  constexpr int kSlotDoubles = nexp * kWarp;                       // TPW records per ring slot
   extern __shared__ __align__(128) char smem[];
   double* ring = reinterpret_cast<double*>(smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(kStages) * kRecBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(kStages) * kSlotDoubles * sizeof(double));
   const int lane = threadIdx.x;
-  const Lane<M, W> L(P, nullptr, blockIdx.x, lane);
+  const int tile0 = blockIdx.x * TPW;
+  const int ntiles = (P.T - tile0 < TPW) ? (P.T - tile0) : TPW;   // tiles of this warp that exist
+  const Lane<M, W> L(P, nullptr, tile0 + lane / W, lane % W);    // a == 0 for every lane
   const DevOptions& o = P.opt;
   const int N = P.N;
-  const bool valid = L.valid && L.a == 0;
+  const bool valid = L.valid;
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  const double* rec0 = P.EXP + static_cast<size_t>(blockIdx.x) * (N + 1) * nexp * W;
+  const size_t tile_stride = static_cast<size_t>(N + 1) * nexp * W;  // doubles between tiles
+  const double* rec0 = P.EXP + static_cast<size_t>(tile0) * tile_stride;
+  auto load_slot = [&](int slot, int k) {  // lane 0 only
+    mbar_expect_tx(&bars[slot], kRecBytes * ntiles);
+    for (int t = 0; t < ntiles; ++t)
+      tma_load_1d(ring + static_cast<size_t>(slot) * kSlotDoubles + t * nexp * W,
+                  rec0 + t * tile_stride + static_cast<size_t>(k) * nexp * W, kRecBytes, &bars[slot]);
+  };
 
   double reg = 0.0, dreg = 0.0, dV0 = 0.0, dV1 = 0.0;
   int st = kUnsolved;
@@ -1129,7 +1138,7 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
   }
   int max_reg_count = 0;
   bool repeat = valid;
-  uint32_t issued = 0, consumed = 0;  // monotonically increasing record counters (warp-uniform)
+  uint32_t issued = 0, consumed = 0;  // monotonically increasing slot counters (warp-uniform)
   while (__any_sync(kFull, repeat)) {
     // terminal cost-to-go: lxx, lx of knot N (plain loads, once per pass)
     double Pm[n * n], p[n];
@@ -1150,21 +1159,13 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
     }
     // prologue: fill the ring
     int next_k = N - 1;
-    if (lane == 0) {
-      for (int s = 0; s < kStages && next_k >= 0; ++s, --next_k, ++issued) {
-        const int slot = issued % kStages;
-        mbar_expect_tx(&bars[slot], kRecBytes);
-        tma_load_1d(ring + static_cast<size_t>(slot) * nexp * W,
-                    rec0 + static_cast<size_t>(next_k) * nexp * W, kRecBytes, &bars[slot]);
-      }
-    }
-    issued = __shfl_sync(kFull, issued, 0);
-    next_k = __shfl_sync(kFull, next_k, 0);
+    for (int s = 0; s < kStages && next_k >= 0; ++s, --next_k, ++issued)
+      if (lane == 0) load_slot(issued % kStages, next_k);
     bool live = repeat;  // lanes still descending in this pass
     for (int k = N - 1; k >= 0; --k, ++consumed) {
       const int slot = consumed % kStages;
       mbar_wait(&bars[slot], (consumed / kStages) & 1);
-      const double* e = ring + static_cast<size_t>(slot) * nexp * W + L.i;
+      const double* e = ring + static_cast<size_t>(slot) * kSlotDoubles + (lane / W) * nexp * W + L.i;
       double A[n * n], B[n * m], lxx[n * n], lxu[n * m], luu[m * m], lx[n], lu[m];
       int f = 0;
       ALTRO_UNROLL
@@ -1183,12 +1184,7 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
       for (int q = 0; q < m; ++q) lu[q] = e[(f++) * W];
       __syncwarp();  // every lane has read the slot -> it can be refilled
       if (next_k >= 0) {
-        if (lane == 0) {
-          const int s2 = issued % kStages;
-          mbar_expect_tx(&bars[s2], kRecBytes);
-          tma_load_1d(ring + static_cast<size_t>(s2) * nexp * W,
-                      rec0 + static_cast<size_t>(next_k) * nexp * W, kRecBytes, &bars[s2]);
-        }
+        if (lane == 0) load_slot(issued % kStages, next_k);
         --next_k;
         ++issued;
       }

@@ -105,6 +105,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(clocks)}
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_backward_mat from the committed ncu capture."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_backward_mat_summary.txt"))):
+        txt = open(path).read()
+        rd = re.search(r"dram__bytes_read\.sum \[Mbyte\] = ([0-9.]+)", txt)
+        wr = re.search(r"dram__bytes_write\.sum \[Mbyte\] = ([0-9.]+)", txt)
+        if rd and wr:
+            best = ((float(rd.group(1)) + float(wr.group(1))) * 1e6, os.path.basename(path))
+    return best
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -317,7 +331,9 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "k_backward_mat (materialised backward pass, TMA-streamed)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         "traffic": (profiled_traffic() or (None, None))[0] if args.workload == "c2" and B == 16384 else None,
+                         "traffic_source": (profiled_traffic() or (None, None))[1],
                          "bytes_per_launch": bp_bytes, "ms_per_launch": ms_bp},
             "solve_kernel": {"kernel": "k_solve (fused persistent AL-iLQR)",
                              "backward_passes_per_step": float(stats[1].item()),

@@ -101,7 +101,7 @@ def test_stepwise_unicycle(gpu, oracle, scenario, al):
             assert sc["alpha"][b] == r.stat("alpha")[-1], f"alpha it={it}"
             Xo, Uo = r.trajectory()
             assert close(Xg[b], Xo, 1e-10) and close(Ug[b], Uo, 1e-10)
-            assert close(res["cost"][b], r.stat("cost")[-1], 1e-11)
+            assert close(res["cost"][b], r.stat("cost")[-1], 1e-9)
     # dual / penalty update
     if al:
         s.update_duals()
