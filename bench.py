@@ -325,8 +325,8 @@ def main():
                        "solved_fraction": float(stats[0].item() / total),
                        "mean_ilqr_iterations": float(stats[1].item() / total),
                        "max_ilqr_iterations": float(stats[2].item())},
-            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": "k_backward_mat (materialised backward pass, TMA-streamed)",

@@ -80,6 +80,18 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("all", "diffs"): diffs()
     if what in ("all", "timings"): timings()
+    if what == "sanitize":
+        # small ragged batches through every kernel (run under compute-sanitizer)
+        for scen, al, B in ((P.K_THREE_OBSTACLES, True, 21), (P.K_TURN90, False, 9)):
+            spec = P.unicycle_problem(scen, N=30)
+            X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+            o = pkg.default_options(); o.max_iterations_inner = 6; o.max_iterations_outer = 3
+            s = pkg.BatchSolver(spec, B, use_constraints=al, options=o); s.set_inputs(X0)
+            (s.solve_al if al else s.solve_ilqr)()
+            s.solve_setup(); s.rollout(); s.cost(); s.update_expansions(); s.backward_pass(); s.forward_pass()
+            s.update_convergence_statistics(); s.backward_pass_fused()
+            if al: s.update_duals(); s.update_penalties()
+            print("sanitize run ok", scen, al, B, s.results()["iters"][:3].tolist())
     if what == "ncu_solve":
         # one k_solve launch of the C2 batch: AL init + rollout + 3 inner iterations of every instance
         spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
