@@ -11,8 +11,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaltro_b200.so")
-SOURCES = ["altro_b200.cu"]
-HEADERS = ["common.cuh", "device.cuh", "kernels.cuh", os.path.join("..", "..", "include", "altro_b200.h")]
+SOURCES = ["altro_b200.cu", "altro_b200_large.cu"]
+# per-source extra flags: the large-state path is compiled without FMA contraction (bit parity)
+EXTRA = {"altro_b200_large.cu": ["-fmad=false"]}
+HEADERS = ["common.cuh", "device.cuh", "kernels.cuh", "large.cuh", os.path.join("..", "..", "include", "altro_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -37,15 +39,27 @@ def build(force: bool = False, verbose: bool = False, out: str = LIB, defines=()
     if out == LIB and not force and not is_stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines] + \
-          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
-    if os.environ.get("ALTRO_B200_FMAD", "1") == "0":
-        cmd.insert(1, "-fmad=false")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+    base = [f for f in NVCC_FLAGS if f != "-shared"]
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build_" + os.path.splitext(src)[0] + ("" if out == LIB else "_" + os.path.basename(out)) + ".o")
+        cmd = [nvcc] + base + EXTRA.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + \
+              [f"-D{d}" for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if os.environ.get("ALTRO_B200_FMAD", "1") == "0" and "-fmad=false" not in cmd:
+            cmd.insert(1, "-fmad=false")
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for cmd, p in procs:
+        log, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(log)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    link = [nvcc, "-shared", "-cudart", "shared", "-o", out] + objs
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libaltro_b200.so")
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed building libaltro_b200.so")
     return out
 
 

@@ -17,6 +17,10 @@
 
 #include "kernels.cuh"
 
+// large-state path, compiled in its own translation unit (altro_b200_large.cu) without FMA
+// contraction so that its ill-conditioned LLT decisions match the CPU oracle bit for bit
+cudaError_t altro_b200_launch_solve_large_32_8(const altro_b200::SolverParams& P, int mode, cudaStream_t st);
+
 using namespace altro_b200;
 
 namespace {
@@ -143,6 +147,7 @@ struct Ops {
   cudaError_t (*phase)(const SolverParams&, int phase, cudaStream_t);
   cudaError_t (*expansions)(const SolverParams&, cudaStream_t);
   cudaError_t (*backward_mat)(const SolverParams&, bool store_ctg, cudaStream_t);
+  bool large = false;  // one instance per CTA (large.cuh): whole solves only, W = 1 layout
 };
 
 constexpr int kBpStages = 4;
@@ -194,6 +199,18 @@ Ops make_ops() {
   return o;
 }
 
+Ops make_large_ops_32_8() {
+  Ops o;
+  o.large = true;
+  o.phase = nullptr;
+  o.expansions = nullptr;
+  o.backward_mat = nullptr;
+  o.solve = [](const SolverParams& P, int mode, int, cudaStream_t st) -> cudaError_t {
+    return altro_b200_launch_solve_large_32_8(P, mode, st);
+  };
+  return o;
+}
+
 template <class M>
 bool ops_for_width(int W, Ops* out) {
   if (W == 2) { if (out) *out = make_ops<M, 2>(); return true; }
@@ -209,6 +226,7 @@ bool lookup_ops(int n, int m, int model, int W, Ops* out) {
   if (model == kTripleIntegrator && n == 6 && m == 2) return ops_for_width<TripleIntegrator<2>>(W, out);
   if (model == kTripleIntegrator && n == 3 && m == 1) return ops_for_width<TripleIntegrator<1>>(W, out);
   if (model == kCartpole && n == 4 && m == 1) return ops_for_width<Cartpole>(W, out);
+  if (model == kLinear && n == 32 && m == 8) { if (out) *out = make_large_ops_32_8(); return true; }
   return false;
 }
 
@@ -553,8 +571,14 @@ int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_con
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
   auto s = std::make_unique<altro_b200_solver>();
   s->n = p->n; s->m = p->m; s->N = p->N; s->B = batch;
-  s->W = choose_tile_width(batch, sm_count);
-  s->G = kWarp / s->W;
+  Ops probe;
+  lookup_ops(p->n, p->m, p->model, 32, &probe);
+  if (probe.large && pmax > 0)
+    return fail(ALTRO_B200_ERR_UNSUPPORTED, "the large-state path (n=32) supports unconstrained problems only");
+  if (probe.large && static_cast<int>(p->params.size()) != p->n * (p->n + p->m))
+    return fail(ALTRO_B200_ERR_ARG, "linear model needs params = [A (n*n), B (n*m)]");
+  s->W = probe.large ? 1 : choose_tile_width(batch, sm_count);
+  s->G = probe.large ? 1 : kWarp / s->W;
   s->T = (batch + s->W - 1) / s->W;
   s->Bp = s->T * s->W;
   s->pmax = pmax;
@@ -753,7 +777,8 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
     CU(cudaStreamSynchronize(st));
     const int unfinished = s->h_count[0];
     if (unfinished == 0) break;
-    if (repack_pct > 0 && static_cast<long>(unfinished) * 100 <= static_cast<long>(cur->B) * repack_pct) {
+    if (!s->ops.large && repack_pct > 0 &&
+        static_cast<long>(unfinished) * 100 <= static_cast<long>(cur->B) * repack_pct) {
       const int nxt = (cur_sec == 0) ? 1 : 0;
       if ((rc = ensure_secondary(s, nxt))) return rc;
       altro_b200_solver::Secondary& w = s->sec[nxt];
@@ -798,6 +823,7 @@ int altro_b200_solve_al_host(altro_b200_solver* s, const double* x0, const doubl
 static int phase_impl(altro_b200_solver* s, int phase, cudaStream_t st) {
   if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
   if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
+  if (s->ops.large) return fail(ALTRO_B200_ERR_UNSUPPORTED, "step-wise methods are not available on the large-state path");
   DeviceGuard guard(s->device);
   int rc = s->ensure_stepwise();
   if (rc) return rc;
@@ -811,6 +837,7 @@ int altro_b200_cost(altro_b200_solver* s, void* stream) { return phase_impl(s, k
 int altro_b200_update_expansions(altro_b200_solver* s, void* stream) {
   if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
   if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
+  if (s->ops.large) return fail(ALTRO_B200_ERR_UNSUPPORTED, "step-wise methods are not available on the large-state path");
   DeviceGuard guard(s->device);
   int rc = s->ensure_stepwise();
   if (rc) return rc;

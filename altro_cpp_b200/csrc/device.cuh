@@ -607,4 +607,17 @@ __device__ __forceinline__ bool riccati_step(const double* A, const double* B, c
   return true;
 }
 
+// IncreaseRegularization / DecreaseRegularization, ilqr.hpp:770-786 (Q4)
+__device__ __forceinline__ void increase_reg(const DevOptions& o, double& reg, double& dreg) {
+  dreg = fmax(dreg * o.bp_reg_increase_factor, o.bp_reg_increase_factor);
+  reg = fmax(reg * dreg, o.bp_reg_min);
+  reg = fmin(reg, o.bp_reg_max);
+}
+__device__ __forceinline__ void decrease_reg(const DevOptions& o, double& reg, double& dreg) {
+  dreg = fmin(dreg / o.bp_reg_increase_factor, 1 / o.bp_reg_increase_factor);
+  reg = fmax(reg * dreg, o.bp_reg_min);
+  reg = fmin(reg, o.bp_reg_max);
+}
+
+
 }  // namespace altro_b200

@@ -101,18 +101,6 @@ __host__ __device__ constexpr int stage_doubles(int pmax, int W) {
   return 2 * (fwd > bwd ? fwd : bwd);
 }
 
-// IncreaseRegularization / DecreaseRegularization, ilqr.hpp:770-786 (Q4)
-__device__ __forceinline__ void increase_reg(const DevOptions& o, double& reg, double& dreg) {
-  dreg = fmax(dreg * o.bp_reg_increase_factor, o.bp_reg_increase_factor);
-  reg = fmax(reg * dreg, o.bp_reg_min);
-  reg = fmin(reg, o.bp_reg_max);
-}
-__device__ __forceinline__ void decrease_reg(const DevOptions& o, double& reg, double& dreg) {
-  dreg = fmin(dreg / o.bp_reg_increase_factor, 1 / o.bp_reg_increase_factor);
-  reg = fmax(reg * dreg, o.bp_reg_min);
-  reg = fmin(reg, o.bp_reg_max);
-}
-
 // ------------------------------------------------------------------------------------------
 // Forward sweep.  kClosed = false: Rollout() in place on Z (zsel) + Cost().
 //                 kClosed = true : RolloutClosedLoop(alpha) from Z (zsel) into buffer zout +

@@ -297,3 +297,45 @@ def perturbed_initial_states(spec: ProblemSpec, B: int, scale, seed: int = 20240
 UNICYCLE_X0_SCALE = (0.3, 0.3, math.pi / 6)
 TRIPLE_INTEGRATOR_X0_SCALE = (0.5,) * 6
 CARTPOLE_X0_SCALE = (0.05,) * 4
+
+
+def random_lqr_problem(n: int = 32, m: int = 8, N: int = 100, seed: int = 5,
+                       literal: bool = False) -> ProblemSpec:
+    """BASELINE config C5: discrete LTI x+ = A x + B u, A = I + g G/sqrt(n),
+    B = 0.1 H, G, H i.i.d. N(0,1) from `seed`; Q = I h, Qf = 10 I, h = 0.05; unconstrained.
+    Not in the reference: parity is GPU vs oracle only.
+
+    literal=True takes SURVEY.md's numbers verbatim (g = 0.05, R = 0.1 h I).  That problem is
+    ill-conditioned (spectral radius 1.05 over 100 steps, cond(Quu) ~ 1e8): the first backward pass
+    fails its LLT at zero regularisation and the solve needs 25-50 iterations instead of the 2 the
+    survey expects.  The default (g = 0.02, R = 0.1 I) is the well-conditioned problem with the
+    intended behaviour: no LLT failure, alpha = 1 accepted, 2 iterations."""
+    rng = np.random.default_rng(seed)
+    G = rng.standard_normal((n, n))
+    Hm = rng.standard_normal((n, m))
+    g = 0.05 if literal else 0.02
+    A = np.eye(n) + g * G / math.sqrt(n)
+    Bm = 0.1 * Hm
+    spec = ProblemSpec(n, m, N, name=f"random-lqr-n{n}-m{m}-N{N}" + ("-literal" if literal else ""))
+    spec.set_model(MODEL_LINEAR, np.concatenate([_colmajor(A), _colmajor(Bm)]))
+    h = np.float32(0.05)
+    spec.set_uniform_step(h)
+    Q = np.eye(n) * float(h)
+    R = np.eye(m) * ((0.1 * float(h)) if literal else 0.1)
+    Qf = np.eye(n) * 10.0
+    xf = np.zeros(n)
+    uref = np.zeros(m)
+    spec.set_cost(0, N, *lqr_cost(Q, R, xf, uref))
+    spec.set_cost(N, N + 1, *lqr_cost(Qf, R * 0, xf, uref))
+    spec.set_initial_state(np.zeros(n))
+    spec.u0 = np.zeros(m)
+    spec.xf = xf
+    return spec
+
+
+def normal_initial_states(spec: ProblemSpec, B: int, seed: int = 20240925, first: int = 0) -> np.ndarray:
+    """x0 ~ N(0, I) per instance from the counter-based generator (Box-Muller on two streams)."""
+    u1 = 0.5 * (uniform_batch(B, spec.n, seed, first) + 1.0)
+    u2 = 0.5 * (uniform_batch(B, spec.n, seed + 1, first) + 1.0)
+    u1 = np.clip(u1, 2.0 ** -53, 1.0)
+    return np.ascontiguousarray(np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * math.pi * u2))

@@ -58,7 +58,8 @@ typedef enum altro_b200_model {
   ALTRO_B200_MODEL_UNICYCLE = 0,          /* examples/unicycle.cpp:12-33, n=3 m=2 */
   ALTRO_B200_MODEL_TRIPLE_INTEGRATOR = 1, /* examples/triple_integrator.cpp:9-33, n=3m */
   ALTRO_B200_MODEL_CARTPOLE = 2,          /* new (BASELINE config C4), params mc,mp,l,g */
-  ALTRO_B200_MODEL_LINEAR = 3             /* new (BASELINE config C5), discrete x+=Ax+Bu */
+  ALTRO_B200_MODEL_LINEAR = 3             /* new (BASELINE config C5), discrete x+=Ax+Bu; n=32, m=8,
+                                             unconstrained, whole solves only (one instance per CTA) */
 } altro_b200_model;
 
 /* altro/common/solver_options.hpp:19-65, numeric fields only (logging/profiler/thread

@@ -82,7 +82,7 @@ def test_stepwise_unicycle(gpu, oracle, scenario, al):
                 for name in ("lxx", "lxu", "luu", "lx", "lu"):
                     assert close(e[name][b], eo[name], 1e-11 if it == 0 else 1e-9), (it, k, name)
                 if True:  # knot N carries IdentityDynamics (problem.hpp:161-164)
-                    assert close(e["A"][b], eo["A"], 1e-10) and close(e["B"][b], eo["B"], 1e-10), (it, k)
+                    assert close(e["A"][b], eo["A"], 1e-12 if it == 0 else 1e-8) and close(e["B"][b], eo["B"], 1e-12 if it == 0 else 1e-8), (it, k)
             r.backward_pass()
             Ko, do = r.gains()
             gtol = 1e-9 if it == 0 else 1e-7
@@ -461,3 +461,24 @@ def test_solve_triple_integrator_full_c3_slice(gpu, oracle):
     assert same.mean() >= 0.95
     idx = np.where(same)[0]
     assert max(rel_err(out["X"][i], ref["X"][i]) for i in idx) <= 1e-8
+
+
+@pytest.mark.parametrize("literal", [False, True])
+def test_solve_random_lqr_c5(gpu, oracle, literal):
+    # BASELINE config C5: n = 32, m = 8, N = 100, unconstrained (one instance per CTA, large.cuh,
+    # compiled without FMA contraction and summing in the oracle's order -> expected bit-equal).
+    # The model is not in the reference: parity is GPU vs oracle only.  literal=True is the
+    # ill-conditioned variant whose LLT decisions hinge on the last bit (problems.py).
+    spec = P.random_lqr_problem(literal=literal)
+    X0 = P.normal_initial_states(spec, 24 if literal else 48)
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, al=True, max_mismatch_frac=0.0)
+    assert np.all(r["status"] == 0)
+    if not literal:
+        assert np.all(r["iters"][:, 0] == 2)
+    for k in ("X", "U", "cost", "K", "d"):
+        assert errs[k] <= 1e-12, errs
+    # step-wise methods are not offered on this path
+    s = gpu.BatchSolver(spec, 4)
+    s.set_inputs(X0[:4])
+    with pytest.raises(gpu.SolverError, match="not available on the large-state path"):
+        s.rollout()

@@ -34,6 +34,7 @@ def test_version_and_support_matrix():
     assert L.altro_b200_is_supported(3, 2, P.MODEL_UNICYCLE) == 1
     assert L.altro_b200_is_supported(6, 2, P.MODEL_TRIPLE_INTEGRATOR) == 1
     assert L.altro_b200_is_supported(4, 1, P.MODEL_CARTPOLE) == 1
+    assert L.altro_b200_is_supported(32, 8, P.MODEL_LINEAR) == 1
     assert L.altro_b200_is_supported(5, 5, P.MODEL_UNICYCLE) == 0
 
 
