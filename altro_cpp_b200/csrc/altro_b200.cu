@@ -753,10 +753,11 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
   if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
   if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
   DeviceGuard guard(s->device);
-  const int budget = std::max(1, env_int("ALTRO_B200_BUDGET", 32));
-  const int repack_pct = env_int("ALTRO_B200_REPACK_PCT", 60);  // 0 disables re-packing
+  const int budget = std::max(1, env_int("ALTRO_B200_BUDGET", 16));
+  const int repack_pct = env_int("ALTRO_B200_REPACK_PCT", 100);  // 0 disables re-packing
   int rc;
   if ((rc = fill_int(s, I_PHASE, mode == 1 ? kPhAlInit : kPhSolveStart, st))) return rc;
+  if ((rc = fill_int(s, I_LSFAIL, 0, st))) return rc;
   k_iota<<<(s->Bp + 255) / 256, 256, 0, st>>>(s->P.is + static_cast<size_t>(I_ORIG) * s->Bp, s->Bp);
   if ((rc = check_launch(s, 1))) return rc;
   SolverParams* cur = &s->P;
@@ -782,7 +783,7 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
       const int nxt = (cur_sec == 0) ? 1 : 0;
       if ((rc = ensure_secondary(s, nxt))) return rc;
       altro_b200_solver::Secondary& w = s->sec[nxt];
-      k_list_unfinished<<<(cur->B + 255) / 256, 256, 0, st>>>(*cur, s->d_list);
+      k_list_unfinished<<<(cur->B + 255) / 256, 256, 0, st>>>(*cur, s->d_list, unfinished);
       if ((rc = check_launch(s, 1))) return rc;
       SolverParams& Q = w.P;
       Q.B = unfinished;

@@ -148,6 +148,7 @@ enum IntField : int {
   I_ZSEL,          // which trajectory buffer currently is Z_ (the others hold line-search candidates)
   I_PHASE,         // SolvePhase: where the instance is in its solve (k_solve is resumable)
   I_ORIG,          // index of the instance in the solver's primary workspace (compaction)
+  I_LSFAIL,        // 1: the instance's last line search failed completely (scheduling hint only)
   I_NUM
 };
 

@@ -369,8 +369,19 @@ __device__ __forceinline__ double al_value(const ConSet& cs, const double* x, co
   for (int bi = 0; bi < cs.nblocks; ++bi) {
     const ConBlock& b = cs.blk[bi];
     double sa = 0.0, sb = 0.0;
+    double px = 0.0, py = 0.0;
+    if (b.kind == kCircle) {  // loop-invariant position of the circle rows
+      px = pick<n>(x, b.xi);
+      py = pick<n>(x, b.yi);
+    }
     for (int i = 0; i < b.p; ++i) {
-      const double c = con_row_fast<n, m>(b, i, x, u);
+      double c;
+      if (b.kind == kCircle) {
+        const double dx = px - b.a[i], dy = py - b.b[i];
+        c = -(dx * dx + dy * dy - b.c[i] * b.c[i]);
+      } else {
+        c = con_row_fast<n, m>(b, i, x, u);
+      }
       const double l = lam[(b.row0 + i) * LS];
       const double arg = l - rho * c;
       const double lp = b.equality ? arg : fmin(0.0, arg);

@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, ALTRO_SOLVE_MINB) k_solve(
   double cost_cur = 0.0, cost_prev = 0.0, initial_cost = 0.0, viol = 0.0;
   double dJ = 0.0, grad = 0.0, alpha_stat = 0.0, z_stat = 0.0, csrc = -1.0, J0 = 0.0;
   int zsel = 0, it_inner = 0, it_outer = 0, it_total = 0, st = kUnsolved, st_al = kUnsolved;
-  int phase = kPhReported;
+  int phase = kPhReported, lsfail = 0;
   if (valid) {
     penalty = L.sc(S_PENALTY);
     reg = L.sc(S_REG);
@@ -616,6 +616,7 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, ALTRO_SOLVE_MINB) k_solve(
     st = L.is(I_STATUS);
     st_al = L.is(I_STATUS_AL);
     phase = L.is(I_PHASE);
+    lsfail = L.is(I_LSFAIL);
   }
   const bool was_reported = phase >= kPhReported;
   if (phase == kPhAlInit) {  // AugmentedLagrangianiLQR::Init, al_solver.hpp:287-302 (Q10)
@@ -711,6 +712,7 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, ALTRO_SOLVE_MINB) k_solve(
       gs_bwd = __shfl_sync(kFull, gs_bwd, L.i);
       const LineSearchResult ls = line_search<M, W>(L, stg, run, zsel, penalty, J0, dV0, dV1, st, csrc);
       if (run) {
+        lsfail = ls.success ? 0 : 1;
         if (ls.success) {
           zsel = Lane<M, W>::cand(zsel, ls.slot);  // (*Z_) = (*Zbar_)
           J0 = ls.J;
@@ -778,6 +780,7 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, ALTRO_SOLVE_MINB) k_solve(
     L.is(I_ITERS_TOTAL) = it_total;
     L.is(I_ZSEL) = zsel;
     L.is(I_PHASE) = phase;
+    L.is(I_LSFAIL) = lsfail;
     if (phase < kPhReported) atomicAdd(&P.counters[0], 1);
   }
 }
@@ -785,13 +788,19 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, ALTRO_SOLVE_MINB) k_solve(
 // ------------------------------------------------------------------------------------------
 // Re-packing of unfinished instances between k_solve launches (runtime tile widths).
 // ------------------------------------------------------------------------------------------
-// list[j] = slot (in `src`) of the j-th unfinished instance; count in src.counters[1]
-__global__ void k_list_unfinished(SolverParams src, int* __restrict__ list) {
+// list[] = slots (in `src`) of the unfinished instances, `total` of them: those whose last line
+// search failed completely are packed from the front, the others from the back, so that tiles of
+// the re-packed workspace are homogeneous (a tile pays for its slowest member's line-search
+// rounds).  Counters: [1] front cursor, [2] back cursor.
+__global__ void k_list_unfinished(SolverParams src, int* __restrict__ list, int total) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= src.B) return;
   if (src.is[static_cast<size_t>(I_PHASE) * src.Bp + b] < kPhReported) {
-    const int j = atomicAdd(&src.counters[1], 1);
-    list[j] = b;
+    if (src.is[static_cast<size_t>(I_LSFAIL) * src.Bp + b]) {
+      list[atomicAdd(&src.counters[1], 1)] = b;
+    } else {
+      list[total - 1 - atomicAdd(&src.counters[2], 1)] = b;
+    }
   }
 }
 

@@ -17,20 +17,24 @@ constexpr int kLargeThreads = 256;
 
 // C (r x c) = op(A) * B ; all column-major in shared memory; each thread owns elements
 // e = tid, tid + T, ... and sums the inner index ascending.
-template <int r, int k, int c, bool kTransA>
+// lda = leading dimension of A (k for a transposed k x r operand unless padded)
+template <int r, int k, int c, bool kTransA, int lda>
 __device__ __forceinline__ void sm_matmul(const double* A, const double* B, double* C) {
   for (int e = threadIdx.x; e < r * c; e += kLargeThreads) {
     const int i = e % r, j = e / r;
-    double acc = (kTransA ? A[i * k] : A[i]) * B[j * k];
-    for (int l = 1; l < k; ++l) acc += (kTransA ? A[l + i * k] : A[i + l * r]) * B[l + j * k];
+    double acc = (kTransA ? A[i * lda] : A[i]) * B[j * k];
+    for (int l = 1; l < k; ++l) acc += (kTransA ? A[l + i * lda] : A[i + l * lda]) * B[l + j * k];
     C[e] = acc;
   }
 }
 
+// A, B and K are also read transposed (A'P, B'P, K'Quu, K'Qxu'): with the natural leading
+// dimension consecutive lanes would hit one bank (stride 32 or 8 doubles), so they are stored
+// with leading dimension n+1 / m+1.
 template <int n, int m>
 struct LargeSmem {
-  double A[n * n], B[n * m], P[n * n], T[n * n], Qxx[n * n], Qxu[n * m], Quu[m * m], L[m * m];
-  double BtP[m * n], K[m * n], KtQuu[n * m];
+  double A[(n + 1) * n], B[(n + 1) * m], P[n * n], T[n * n], Qxx[n * n], Qxu[n * m], Quu[m * m], L[m * m];
+  double BtP[m * n], K[(m + 1) * n], KtQuu[n * m];
   double x[n], xr[n], u[m], p[n], Qx[n], Qu[m], d[m], lx[n], lu[m], v1[n], v2[n], v3[n], tmp[n];
   double scal[16];
   int iscal[8];
@@ -43,7 +47,7 @@ __global__ void __launch_bounds__(kLargeThreads) k_solve_large(SolverParams P, i
   LargeSmem<n, m>& S = *reinterpret_cast<LargeSmem<n, m>*>(smem_raw);
   const int b = blockIdx.x, tid = threadIdx.x;
   if (b >= P.B) return;
-  constexpr int nz = n + m, nkd = m * n + m;
+  constexpr int nz = n + m, nkd = m * n + m, LA = n + 1, LK = m + 1;
   const Desc D(P.blob);  // read through L1/L2: shared by all CTAs
   const DevOptions& o = P.opt;
   const int N = P.N;
@@ -51,8 +55,8 @@ __global__ void __launch_bounds__(kLargeThreads) k_solve_large(SolverParams P, i
   auto zptr = [&](int sel, int k) { return P.Z[sel] + (static_cast<size_t>(b) * (N + 1) + k) * nz; };
   auto kdptr = [&](int k) { return P.KD + (static_cast<size_t>(b) * N + k) * nkd; };
   double& rsc_cost = P.sc[static_cast<size_t>(S_COST) * P.Bp + b];
-  for (int e = tid; e < n * n; e += kLargeThreads) S.A[e] = mp[e];
-  for (int e = tid; e < n * m; e += kLargeThreads) S.B[e] = mp[n * n + e];
+  for (int e = tid; e < n * n; e += kLargeThreads) S.A[e % n + (e / n) * LA] = mp[e];
+  for (int e = tid; e < n * m; e += kLargeThreads) S.B[e % n + (e / n) * LA] = mp[n * n + e];
   __syncthreads();
 
   // ---- cost of one knot (QuadraticCost::Evaluate), result in S.scal[15]; x, u in S.x, S.u
@@ -127,9 +131,9 @@ __global__ void __launch_bounds__(kLargeThreads) k_solve_large(SolverParams P, i
         }
         if (tid < n) {  // x+ = A x + B u
           double acc = S.A[tid] * S.x[0];
-          for (int j = 1; j < n; ++j) acc += S.A[tid + j * n] * S.x[j];
+          for (int j = 1; j < n; ++j) acc += S.A[tid + j * LA] * S.x[j];
           double accb = S.B[tid] * S.u[0];
-          for (int j = 1; j < m; ++j) accb += S.B[tid + j * n] * S.u[j];
+          for (int j = 1; j < m; ++j) accb += S.B[tid + j * LA] * S.u[j];
           S.tmp[tid] = acc + accb;
         }
         __syncthreads();
@@ -205,35 +209,35 @@ __global__ void __launch_bounds__(kLargeThreads) k_solve_large(SolverParams P, i
           S.lu[i] = a + r[i] + h2;
         }
         // CalcActionValueExpansion (knot_point_function_type.hpp:149-164)
-        sm_matmul<n, n, n, true>(S.A, S.P, S.T);    // T = A'P
-        sm_matmul<m, n, n, true>(S.B, S.P, S.BtP);  // B'P
+        sm_matmul<n, n, n, true, LA>(S.A, S.P, S.T);    // T = A'P
+        sm_matmul<m, n, n, true, LA>(S.B, S.P, S.BtP);  // B'P
         __syncthreads();
         for (int e = tid; e < n * n; e += kLargeThreads) {
           const int i = e % n, j = e / n;
-          double acc = S.T[i] * S.A[j * n];
-          for (int l = 1; l < n; ++l) acc += S.T[i + l * n] * S.A[l + j * n];
+          double acc = S.T[i] * S.A[j * LA];
+          for (int l = 1; l < n; ++l) acc += S.T[i + l * n] * S.A[l + j * LA];
           S.Qxx[e] = Q[e] + acc;
         }
         for (int e = tid; e < n * m; e += kLargeThreads) {
           const int i = e % n, j = e / n;
-          double acc = S.T[i] * S.B[j * n];
-          for (int l = 1; l < n; ++l) acc += S.T[i + l * n] * S.B[l + j * n];
+          double acc = S.T[i] * S.B[j * LA];
+          for (int l = 1; l < n; ++l) acc += S.T[i + l * n] * S.B[l + j * LA];
           S.Qxu[e] = H[e] + acc;
         }
         for (int e = tid; e < m * m; e += kLargeThreads) {
           const int i = e % m, j = e / m;
-          double acc = S.BtP[i] * S.B[j * n];
-          for (int l = 1; l < n; ++l) acc += S.BtP[i + l * m] * S.B[l + j * n];
+          double acc = S.BtP[i] * S.B[j * LA];
+          for (int l = 1; l < n; ++l) acc += S.BtP[i + l * m] * S.B[l + j * LA];
           S.Quu[e] = R[e] + acc;
         }
         if (tid < n) {
-          double acc = S.A[tid * n] * S.p[0];
-          for (int l = 1; l < n; ++l) acc += S.A[l + tid * n] * S.p[l];
+          double acc = S.A[tid * LA] * S.p[0];
+          for (int l = 1; l < n; ++l) acc += S.A[l + tid * LA] * S.p[l];
           S.Qx[tid] = S.lx[tid] + acc;
         } else if (tid >= 64 && tid < 64 + m) {
           const int i = tid - 64;
-          double acc = S.B[i * n] * S.p[0];
-          for (int l = 1; l < n; ++l) acc += S.B[l + i * n] * S.p[l];
+          double acc = S.B[i * LA] * S.p[0];
+          for (int l = 1; l < n; ++l) acc += S.B[l + i * LA] * S.p[l];
           S.Qu[i] = S.lu[i] + acc;
         }
         __syncthreads();
@@ -293,30 +297,30 @@ __global__ void __launch_bounds__(kLargeThreads) k_solve_large(SolverParams P, i
             bv[i] = s / S.L[i + i * m];
           }
           for (int i = 0; i < m; ++i) {
-            if (tid < n) S.K[i + tid * m] = bv[i] * -1;
+            if (tid < n) S.K[i + tid * LK] = bv[i] * -1;
             else S.d[i] = bv[i] * -1;
           }
         }
         __syncthreads();
         // CalcCostToGo (unregularised Q, Q3)
-        sm_matmul<n, m, m, true>(S.K, S.Quu, S.KtQuu);  // K'Quu (n x m)
+        sm_matmul<n, m, m, true, LK>(S.K, S.Quu, S.KtQuu);  // K'Quu (n x m)
         __syncthreads();
         if (tid < n) {
-          double a1 = S.KtQuu[tid] * S.d[0], a2 = S.K[tid * m] * S.Qu[0], a3 = S.Qxu[tid] * S.d[0];
+          double a1 = S.KtQuu[tid] * S.d[0], a2 = S.K[tid * LK] * S.Qu[0], a3 = S.Qxu[tid] * S.d[0];
           for (int l = 1; l < m; ++l) {
             a1 += S.KtQuu[tid + l * n] * S.d[l];
-            a2 += S.K[l + tid * m] * S.Qu[l];
+            a2 += S.K[l + tid * LK] * S.Qu[l];
             a3 += S.Qxu[tid + l * n] * S.d[l];
           }
           S.tmp[tid] = S.Qx[tid] + a1 + a2 + a3;
         }
         for (int e = tid; e < n * n; e += kLargeThreads) {
           const int i = e % n, j = e / n;
-          double t1 = S.KtQuu[i] * S.K[j * m], t2 = S.K[i * m] * S.Qxu[j], t3 = S.Qxu[i] * S.K[j * m];
+          double t1 = S.KtQuu[i] * S.K[j * LK], t2 = S.K[i * LK] * S.Qxu[j], t3 = S.Qxu[i] * S.K[j * LK];
           for (int l = 1; l < m; ++l) {
-            t1 += S.KtQuu[i + l * n] * S.K[l + j * m];
-            t2 += S.K[l + i * m] * S.Qxu[j + l * n];
-            t3 += S.Qxu[i + l * n] * S.K[l + j * m];
+            t1 += S.KtQuu[i + l * n] * S.K[l + j * LK];
+            t2 += S.K[l + i * LK] * S.Qxu[j + l * n];
+            t3 += S.Qxu[i + l * n] * S.K[l + j * LK];
           }
           S.T[e] = S.Qxx[e] + t1 + t2 + t3;  // new P (into T, swapped below)
         }
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(kLargeThreads) k_solve_large(SolverParams P, i
           gs += g;
         }
         double* pk = kdptr(k);
-        for (int e = tid; e < m * n; e += kLargeThreads) pk[e] = S.K[e];
+        for (int e = tid; e < m * n; e += kLargeThreads) pk[e] = S.K[e % m + (e / m) * LK];
         if (tid < m) pk[m * n + tid] = S.d[tid];
         __syncthreads();
         if (k == 0) repeat = false;

@@ -39,15 +39,21 @@ UNIT = "solves/s"
 
 
 def workload(name: str):
+    """-> (spec, x0 generator (spec, count) -> [count, n], default batch per GPU, description)."""
+    pert = lambda scale: (lambda spec, count: P.perturbed_initial_states(spec, count, scale))
     if name == "c2":
-        return P.unicycle_problem(P.K_THREE_OBSTACLES), P.UNICYCLE_X0_SCALE, 16384, \
+        return P.unicycle_problem(P.K_THREE_OBSTACLES), pert(P.UNICYCLE_X0_SCALE), 16384, \
             "C2: unicycle n=3 m=2 N=100, 3 obstacles + control bounds + goal, AL-iLQR, default options"
     if name == "c3":
-        return P.triple_integrator_problem(dof=2, N=50, add_constraints=True), P.TRIPLE_INTEGRATOR_X0_SCALE, \
+        return P.triple_integrator_problem(dof=2, N=50, add_constraints=True), pert(P.TRIPLE_INTEGRATOR_X0_SCALE), \
             8192, "C3: triple integrator n=6 m=2 N=50, goal + control bounds, AL-iLQR (8192 per GPU)"
     if name == "c4":
-        return P.cartpole_problem(N=200), P.CARTPOLE_X0_SCALE, 32768, \
+        return P.cartpole_problem(N=200), pert(P.CARTPOLE_X0_SCALE), 32768, \
             "C4: cartpole n=4 m=1 N=200, control bound, AL-iLQR"
+    if name in ("c5", "c5-literal"):
+        return P.random_lqr_problem(literal=name.endswith("literal")), P.normal_initial_states, 4096, \
+            "C5: random LQR n=32 m=8 N=100, unconstrained (" + \
+            ("SURVEY.md numbers verbatim, ill-conditioned" if name.endswith("literal") else "well-conditioned variant") + ")"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -161,7 +167,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    spec, scale, default_B, wl_name = workload(args.workload)
+    spec, gen_x0, default_B, wl_name = workload(args.workload)
     B = args.batch or default_B
     ncores = os.cpu_count() or 1
 
@@ -169,7 +175,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        X0 = P.perturbed_initial_states(spec, B, scale)
+        X0 = gen_x0(spec, B)
         sample = min(args.cpu_sample, B)
         W = max(0, args.warmup)
         val, dt, out = cpu_leg(spec, X0, args.steps, W, sample, ncores)
@@ -208,7 +214,7 @@ def main():
     total = B * world
     X0_all_dev = None
     if rank == 0:
-        X0_all_dev = torch.from_numpy(P.perturbed_initial_states(spec, total, scale)).to(dev)
+        X0_all_dev = torch.from_numpy(gen_x0(spec, total)).to(dev)
     if distributed:
         x0_dev = scatter_rows(X0_all_dev, total, (n,), torch.float64, dev)
     else:
@@ -268,7 +274,10 @@ def main():
     d2h = B * ((N + 1) * n + N * m) * 8 + B * (8 + 8 + 4 + 12)
 
     # ---- roofline: the materialised backward-pass kernel, timed live
+    ms_bp = float('nan')
+    bp_bytes = solver.backward_pass_bytes()
     with torch.cuda.stream(stream):
+      if not args.workload.startswith('c5'):
         solver.set_inputs_dev(x0_dev.data_ptr(), 0, unom, stream=stream)
         solver.solve_setup(stream=stream)
         solver.rollout(stream=stream)
@@ -286,10 +295,11 @@ def main():
         ms_bp = e4.elapsed_time(e5) / args.bp_iters
     bp_bytes = solver.backward_pass_bytes()
     peak, peak_src = measured_peak()
-    achieved = bp_bytes / (ms_bp * 1e-3) / 1e9
+    have_bp = ms_bp == ms_bp
+    achieved = bp_bytes / (ms_bp * 1e-3) / 1e9 if have_bp else None
 
     # ---- reduce over ranks: max time, summed work
-    t = torch.tensor([ms, ms_e2e, ms_bp], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_bp if have_bp else 0.0], dtype=torch.float64, device=dev)
     stats = torch.tensor([float((res["status"] == 0).sum()), float(res["iters"][:, 2].sum()),
                           float(res["iters"][:, 2].max())], dtype=torch.float64, device=dev)
     if distributed:
@@ -329,7 +339,7 @@ def main():
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_backward_mat (materialised backward pass, TMA-streamed)",
+            "roofline": None if not have_bp else {"kernel": "k_backward_mat (materialised backward pass, TMA-streamed)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          "traffic": (profiled_traffic() or (None, None))[0] if args.workload == "c2" and B == 16384 else None,
