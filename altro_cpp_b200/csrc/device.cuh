@@ -60,6 +60,24 @@ __device__ __forceinline__ void mattmul(const double* A, const double* B, double
 struct Unicycle {  // examples/unicycle.cpp:12-33
   static constexpr int n = 3, m = 2;
   static constexpr bool kDiscrete = false;
+  // value and Jacobian at the same point share one sin/cos evaluation (same results)
+  static __device__ __forceinline__ void eval_jac(const double*, const double* x, const double* u,
+                                                  double* xd, double* A, double* B) {
+    double s, c;
+    sincos(x[2], &s, &c);
+    xd[0] = u[0] * c;
+    xd[1] = u[0] * s;
+    xd[2] = u[1];
+    ALTRO_UNROLL
+    for (int i = 0; i < 9; ++i) A[i] = 0.0;
+    ALTRO_UNROLL
+    for (int i = 0; i < 6; ++i) B[i] = 0.0;
+    A[0 + 2 * 3] = -u[0] * s;
+    A[1 + 2 * 3] = u[0] * c;
+    B[0 + 0 * 3] = c;
+    B[1 + 0 * 3] = s;
+    B[2 + 1 * 3] = 1.0;
+  }
   static __device__ __forceinline__ void eval(const double*, const double* x, const double* u,
                                               double* xd) {
     double s, c;
@@ -156,6 +174,23 @@ struct Cartpole {  // definition owned by this repo; oracle: altro_o
   }
 };
 
+// value + Jacobian of a continuous model at one point; models may provide a fused eval_jac
+template <class M, class = void>
+struct EvalJac {
+  static __device__ __forceinline__ void run(const double* P, const double* x, const double* u, double* xd,
+                                             double* A, double* B) {
+    M::eval(P, x, u, xd);
+    M::jac(P, x, u, A, B);
+  }
+};
+template <class M>
+struct EvalJac<M, decltype((void)&M::eval_jac)> {
+  static __device__ __forceinline__ void run(const double* P, const double* x, const double* u, double* xd,
+                                             double* A, double* B) {
+    M::eval_jac(P, x, u, xd, A, B);
+  }
+};
+
 // RungeKutta4::Integrate, altro/problem/integration.hpp:124-131.  h is float, promoted (Q1).
 template <class M>
 __device__ __forceinline__ void rk4_step(const double* P, const double* x, const double* u,
@@ -188,8 +223,7 @@ __device__ __forceinline__ void rk4_jacobian(const double* P, const double* x, c
   double k1[n], k2[n], k3[n], xt[n];
   double As[n * n], Bs[n * m], dA[n * n], dB[n * m], T[n * n], T2[n * n], TB[n * m];
   // stage 0
-  M::eval(P, x, u, k1);
-  M::jac(P, x, u, As, Bs);
+  EvalJac<M>::run(P, x, u, k1, As, Bs);
   ALTRO_UNROLL
   for (int i = 0; i < n * n; ++i) { dA[i] = As[i] * h; A[i] = dA[i]; }
   ALTRO_UNROLL
@@ -197,8 +231,7 @@ __device__ __forceinline__ void rk4_jacobian(const double* P, const double* x, c
   // stage 1: x + 0.5*k1*h
   ALTRO_UNROLL
   for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * 0.5 * h;
-  M::eval(P, xt, u, k2);
-  M::jac(P, xt, u, As, Bs);
+  EvalJac<M>::run(P, xt, u, k2, As, Bs);
   ALTRO_UNROLL
   for (int j = 0; j < n; ++j)
     ALTRO_UNROLL
@@ -214,8 +247,7 @@ __device__ __forceinline__ void rk4_jacobian(const double* P, const double* x, c
   // stage 2: x + 0.5*k2*h
   ALTRO_UNROLL
   for (int i = 0; i < n; ++i) xt[i] = x[i] + k2[i] * 0.5 * h;
-  M::eval(P, xt, u, k3);
-  M::jac(P, xt, u, As, Bs);
+  EvalJac<M>::run(P, xt, u, k3, As, Bs);
   ALTRO_UNROLL
   for (int j = 0; j < n; ++j)
     ALTRO_UNROLL

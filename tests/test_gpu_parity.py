@@ -482,3 +482,40 @@ def test_solve_random_lqr_c5(gpu, oracle, literal):
     s.set_inputs(X0[:4])
     with pytest.raises(gpu.SolverError, match="not available on the large-state path"):
         s.rollout()
+
+
+def test_warm_start_resolve_keeps_duals_and_penalties(gpu, oracle):
+    """MPC-style re-solve (docs/Overview.dox:49-54; solver_options.hpp:47-48): second Solve() from
+    the previous solution with reset_duals = false and initial_penalty = 0 keeps duals and
+    penalties (al_solver.hpp:292-297).  Compared instance by instance with the oracle."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    B = 40
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, B)
+    s.set_inputs(X0)
+    s.solve_al()
+    first = s.results()
+    o = gpu.default_options()
+    o.reset_duals = 0
+    o.initial_penalty = 0.0
+    s.set_options(o)
+    s.solve_al()
+    r = s.results()
+    Xg, Ug = s.trajectory()
+    pen = s.scalars()["penalty"]
+    for b in (0, 3, 17, 39):
+        ref = oracle.OracleSolver(spec, use_constraints=True)
+        ref.set_initial_state(X0[b])
+        ref.solve_al()
+        assert ref.status()["iterations_total"] == first["iters"][b, 2]
+        oo = oracle.default_options()
+        oo.reset_duals = 0
+        oo.initial_penalty = 0.0
+        ref.set_options(oo)
+        ref.solve_al()
+        st = ref.status()
+        assert (st["iterations_inner"], st["iterations_outer"], st["iterations_total"]) == tuple(r["iters"][b])
+        assert st["status"] == r["status"][b]
+        Xo, Uo = ref.trajectory()
+        assert close(Xg[b], Xo, 1e-8) and close(Ug[b], Uo, 1e-8)
+        assert pen[b] == ref.max_penalty()

@@ -56,6 +56,24 @@ def main(rep, out):
             lines.append(f"    {r[idx['# Samples']]:>7} {r[idx['Instructions Executed']]:>10}  {r[idx['Source']].strip()[:110]}")
         tma = sum(int(r[idx["Instructions Executed"]]) for r in rows if "UBLKCP" in r[idx["Source"]])
         lines.append(f"  UBLKCP (TMA bulk copy) instructions executed: {tma}")
+    # source-level view (needs -lineinfo and --import-source on): per-source-line aggregates
+    cu = list(csv.reader(io.StringIO(run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]))))
+    agg, fname, hdr = [], "?", None
+    for r in cu:
+        if len(r) >= 2 and r[0] in ("File Path", "File Name"):
+            fname = r[1].split("/")[-1]
+        elif len(r) > 8 and r[0] == "Line No":
+            hdr = r
+        elif hdr is not None and len(r) == len(hdr) and r[2] == "-":
+            i_inst, i_samp = hdr.index("Instructions Executed"), hdr.index("# Samples")
+            agg.append((fname, r[0], r[1].strip(), int(r[i_inst] or 0), int(r[i_samp] or 0)))
+    if agg:
+        tot_i = sum(a[3] for a in agg) or 1
+        tot_s = sum(a[4] for a in agg) or 1
+        lines.append(f"== CUDA source lines with metrics: {len(agg)}")
+        lines.append("  top source lines by executed warp-instructions (% instr, % stall samples, file:line, text):")
+        for a in sorted(agg, key=lambda a: -a[3])[:80]:
+            lines.append(f"    {100 * a[3] / tot_i:5.2f} {100 * a[4] / tot_s:5.2f}  {a[0]}:{a[1]:<5} {a[2][:110]}")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[:12]))
 
