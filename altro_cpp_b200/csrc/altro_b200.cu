@@ -275,6 +275,7 @@ struct altro_b200_solver {
     SolverParams P;
     Ops ops;
     bool allocated = false;
+    size_t zcap[kMaxZ] = {};  // instances each trajectory buffer has room for
   } sec[2];
   int* d_list = nullptr;
   int* h_count = nullptr;  // pinned
@@ -632,6 +633,9 @@ void altro_b200_solver_destroy(altro_b200_solver* s) {
   if (!s) return;
   DeviceGuard guard(s->device);
   for (void* p : s->allocs) cudaFree(p);
+  for (auto& w : s->sec)
+    for (int zb = 0; zb < kMaxZ; ++zb)
+      if (w.P.Z[zb]) cudaFree(w.P.Z[zb]);
   if (s->d_io) cudaFree(s->d_io);
   if (s->h_count) cudaFreeHost(s->h_count);
   delete s;
@@ -727,16 +731,28 @@ static int ensure_secondary(altro_b200_solver* s, int which) {
   return 0;
 }
 
-// trajectory buffers 0 .. nbuf-1 of a secondary workspace
-static int ensure_secondary_buffers(altro_b200_solver* s, int which, int nbuf) {
+// trajectory buffers 0 .. nbuf-1 of a secondary workspace, each with room for `count` instances
+// (+ one tile of padding).  Narrow tiles need many buffers but hold few instances, wide tiles the
+// opposite, so the footprint stays ~(W + 32) * 2000 instance-trajectories whatever the batch.
+static int ensure_secondary_buffers(altro_b200_solver* s, int which, int nbuf, int count) {
   altro_b200_solver::Secondary& w = s->sec[which];
-  const int cap = s->Bp + kWarp;
-  const size_t bytes = static_cast<size_t>(cap) * (s->N + 1) * (s->n + s->m) * sizeof(double);
+  const size_t need = static_cast<size_t>(count) + kWarp;
+  const size_t per_instance = static_cast<size_t>(s->N + 1) * (s->n + s->m) * sizeof(double);
   for (int zb = 0; zb < nbuf; ++zb) {
-    if (w.P.Z[zb]) continue;
-    int rc = s->alloc(reinterpret_cast<void**>(&w.P.Z[zb]), bytes);
-    if (rc) return rc;
-    cudaMemset(w.P.Z[zb], 0, bytes);
+    if (w.P.Z[zb] && w.zcap[zb] >= need) continue;
+    if (w.P.Z[zb]) {
+      cudaFree(w.P.Z[zb]);
+      s->dev_bytes -= w.zcap[zb] * per_instance;
+      w.P.Z[zb] = nullptr;
+    }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&w.P.Z[zb]), need * per_instance);
+    if (e != cudaSuccess) {
+      w.zcap[zb] = 0;
+      return fail(ALTRO_B200_ERR_CUDA, std::string("cudaMalloc(re-pack buffer): ") + cudaGetErrorString(e));
+    }
+    w.zcap[zb] = need;
+    s->dev_bytes += need * per_instance;
+    cudaMemset(w.P.Z[zb], 0, need * per_instance);
   }
   return 0;
 }
@@ -788,7 +804,7 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
       SolverParams& Q = w.P;
       Q.B = unfinished;
       Q.W = choose_tile_width(unfinished, s->sm_count);
-      if ((rc = ensure_secondary_buffers(s, nxt, 1 + kWarp / Q.W))) return rc;
+      if ((rc = ensure_secondary_buffers(s, nxt, 1 + kWarp / Q.W, unfinished))) return rc;
       Q.T = (unfinished + Q.W - 1) / Q.W;
       Q.Bp = Q.T * Q.W;
       Q.N = s->N; Q.n = s->n; Q.m = s->m; Q.pmax = s->pmax; Q.use_al = s->use_al;

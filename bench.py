@@ -135,6 +135,16 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_leg(spec, X0, steps, warmup, sample, nthreads):
     """Times the CPU oracle (port of the reference algorithm) on a bounded sample."""
     from oracle import binding as ob
@@ -186,7 +196,7 @@ def main():
             "config": {"workload": wl_name, "batch_per_step": sample,
                        "note": "CPU path of the reference algorithm (oracle port; the reference cannot be "
                                "built here: Eigen absent), one independent solve per host thread"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "cpu_model": cpu_model(),
                              "sample": f"first {sample} instances of the {B}-instance batch per step"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -319,8 +329,11 @@ def main():
         val, dt, out = cpu_leg(spec, X0_host, 1, 0, sample, ncores)
         same = float(np.mean(np.all(out["iters"] == res["iters"][:sample], axis=1)
                              & (out["status"] == res["status"][:sample])))
-        cpu = {"value": val, "unit": UNIT, "cores": ncores, "kind": "port",
+        n1 = min(48, sample)
+        val1, dt1, _ = cpu_leg(spec, X0_host, 1, 0, n1, 1)
+        cpu = {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "cpu_model": cpu_model(),
                "sample": f"first {sample} instances of rank 0's batch, one pass ({dt:.1f} s)",
+               "single_thread_value": val1, "single_thread_sample": f"first {n1} instances ({dt1:.1f} s)",
                "same_status_and_iterations_as_gpu": same}
 
     if rank == 0:
