@@ -26,7 +26,7 @@ h = hashlib.sha1(r["cost"].tobytes() + r["iters"].tobytes()).hexdigest()[:12]
 print(json.dumps(dict(ms=ms, solves_per_s=B / ms * 1e3, solved=float((r["status"] == 0).mean()),
                       mean_iters=float(r["iters"][:, 2].mean()), hash=h)))
 ''' % ROOT
-configs = [("", "", "16", "100"), ("", "", "8", "100"), ("", "", "32", "100"), ("", "", "16", "60"), ("", "", "32", "60")]
+configs = [("", "", "16", "100"), ("", "", "32", "60")]
 for lib, tile, budget, repack in configs:
     env = dict(os.environ)
     if lib:
