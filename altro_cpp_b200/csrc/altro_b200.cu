@@ -233,23 +233,26 @@ bool lookup_ops(int n, int m, int model, int W, Ops* out) {
 // Tile width: the serial sweeps are latency-bound, so a B200 wants >= ~14 warps per SM in flight.
 // Narrow tiles turn a small batch into more warps and free lane groups for the parallel line
 // search; a batch that already fills the machine uses full-width tiles.
+// Warps of the solve kernel that fit on one SM at its register budget (kernels.cuh:
+// ALTRO_SOLVE_MINB blocks of ALTRO_SOLVE_WARPS warps; narrow tiles get the full register file).
+int resident_warps_per_sm(int W) {
+  return (W <= 4 ? ALTRO_SOLVE_MINB_NARROW : ALTRO_SOLVE_MINB) * ALTRO_SOLVE_WARPS;
+}
+
+// Tile width: the narrowest tile (most warps, most lane groups for the parallel line search and
+// the knot-parallel backward sweep) whose warps are all resident at once — a second wave would
+// double the makespan of these latency-bound sweeps.
 int choose_tile_width(int batch, int sm_count) {
   if (const char* e = std::getenv("ALTRO_B200_TILE")) {
     const int w = std::atoi(e);
     if (w == 2 || w == 4 || w == 8 || w == 16 || w == 32) return w;
   }
-  // widest tile that still yields ~14 warps per SM; never more warps than can be resident
-  // together (16 per SM at the solve kernel's register budget), never narrower than 2.
-  const long want = static_cast<long>(sm_count) * 14, resident = static_cast<long>(sm_count) * 16;
+  int pick = 32;
   for (int w = 32; w >= 2; w /= 2) {
     const long warps = (batch + w - 1) / w;
-    if (warps >= want || w == 2) {
-      int pick = w;
-      while (pick < 32 && (batch + pick - 1) / pick > resident) pick *= 2;
-      return pick;
-    }
+    if (warps <= static_cast<long>(sm_count) * resident_warps_per_sm(w)) pick = w;
   }
-  return 8;
+  return pick;
 }
 
 }  // namespace
@@ -804,6 +807,10 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
       SolverParams& Q = w.P;
       Q.B = unfinished;
       Q.W = choose_tile_width(unfinished, s->sm_count);
+      {
+        const int w2 = env_int("ALTRO_B200_TILE2", 0);  // experiment knob: tile width of re-packed workspaces
+        if ((w2 == 2 || w2 == 4 || w2 == 8 || w2 == 16) && (unfinished + w2 - 1) / w2 <= s->sm_count * 16) Q.W = w2;
+      }
       if ((rc = ensure_secondary_buffers(s, nxt, 1 + kWarp / Q.W, unfinished))) return rc;
       Q.T = (unfinished + Q.W - 1) / Q.W;
       Q.Bp = Q.T * Q.W;

@@ -29,6 +29,11 @@
 #ifndef ALTRO_SOLVE_MINB
 #define ALTRO_SOLVE_MINB 7
 #endif
+// register budget of the narrow-tile instantiations (W <= 4), which only run on re-packed
+// workspaces with few warps
+#ifndef ALTRO_SOLVE_MINB_NARROW
+#define ALTRO_SOLVE_MINB_NARROW 4
+#endif
 
 namespace altro_b200 {
 
@@ -571,7 +576,7 @@ __device__ __forceinline__ LineSearchResult line_search(const Lane<M, W>& L, dou
 constexpr int kSolveWarps = ALTRO_SOLVE_WARPS;
 
 template <class M, int W>
-__global__ void __launch_bounds__(kSolveWarps* kWarp, ALTRO_SOLVE_MINB) k_solve(SolverParams P, int mode,
+__global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB_NARROW : ALTRO_SOLVE_MINB)) k_solve(SolverParams P, int mode,
                                                                                int budget) {
   extern __shared__ __align__(128) char smem[];
   copy_blob(P.blob, smem, P.blob_bytes);

@@ -26,8 +26,9 @@ h = hashlib.sha1(r["cost"].tobytes() + r["iters"].tobytes()).hexdigest()[:12]
 print(json.dumps(dict(ms=ms, solves_per_s=B / ms * 1e3, solved=float((r["status"] == 0).mean()),
                       mean_iters=float(r["iters"][:, 2].mean()), hash=h)))
 ''' % ROOT
-configs = [("", "", "16", "100"), ("", "", "32", "60")]
-for lib, tile, budget, repack in configs:
+configs = [("", "", "16", "100", "0"), ("", "", "16", "100", "4"), ("", "", "32", "100", "0"), ("", "", "8", "100", "0"),
+           ("variants/lib_p4.so", "16", "16", "100", "0"), ("variants/lib_p4.so", "16", "16", "100", "4")]
+for lib, tile, budget, repack, tile2 in configs:
     env = dict(os.environ)
     if lib:
         env["ALTRO_B200_LIB"] = os.path.join(ROOT, "altro_cpp_b200", lib)
@@ -35,9 +36,10 @@ for lib, tile, budget, repack in configs:
         env["ALTRO_B200_TILE"] = tile
     env["ALTRO_B200_BUDGET"] = budget
     env["ALTRO_B200_REPACK_PCT"] = repack
+    env["ALTRO_B200_TILE2"] = tile2
     try:
         out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=300)
         line = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-600:]
     except subprocess.TimeoutExpired:
         line = "TIMEOUT"
-    print(f"lib={lib or 'default':10s} tile={tile or 'auto':>4s} budget={budget:>3s} repack={repack:>3s}  {line}", flush=True)
+    print(f"lib={lib or 'default':20s} tile2={tile2:>2s} budget={budget:>3s} repack={repack:>3s}  {line}", flush=True)
