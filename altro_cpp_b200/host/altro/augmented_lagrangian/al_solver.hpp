@@ -1,0 +1,103 @@
+// altro/augmented_lagrangian/al_solver.hpp (B200 host mirror) — AugmentedLagrangianiLQR<n,m>
+// (reference: altro/augmented_lagrangian/al_solver.hpp:28-440) for one instance, and
+// BatchedAugmentedLagrangianiLQR<n,m>, the form the device is built for: B instances of one
+// problem that differ in initial state, solved by one set of kernel launches.
+//
+//   Solve()            al_solver.hpp:304   altro_b200_solve_al
+//   UpdateDuals()                 :336     altro_b200_update_duals
+//   UpdatePenalties()             :347     altro_b200_update_penalties
+//   SetPenalty(rho)               :271     altro_b200_solver_set_penalty
+//   MaxViolation()                :417     altro_b200_get_results_host (viol)
+#pragma once
+
+#include <memory>
+#include <utility>
+#include <vector>
+
+#include "altro/ilqr/ilqr.hpp"
+
+namespace altro {
+namespace augmented_lagrangian {
+
+template <int n, int m>
+class AugmentedLagrangianiLQR {
+ public:
+  explicit AugmentedLagrangianiLQR(const problem::Problem& prob, int device = 0)
+      : core_(std::make_shared<detail::DeviceSolver>(prob, prob.GetDynamics(0)->StateDimension(),
+                                                     prob.GetDynamics(0)->ControlDimension(), true, 1, device)),
+        ilqr_solver_(core_) {}
+
+  void SetTrajectory(std::shared_ptr<Trajectory<n, m>> traj) { ilqr_solver_.SetTrajectory(std::move(traj)); }
+  ilqr::iLQR<n, m>& GetiLQRSolver() { return ilqr_solver_; }
+  SolverOptions& GetOptions() { return core_->GetOptions(); }
+  SolverStats& GetStats() { return core_->GetStats(); }
+  SolverStatus GetStatus() { return static_cast<SolverStatus>(core_->Pull().status[0]); }
+  int NumSegments() const { return core_->NumSegments(); }
+
+  void SetPenalty(double rho) { core_->SetPenalty(rho); }
+  void SetPenaltyScaling(double phi) { core_->SetPenaltyScaling(phi); }
+
+  void Solve() {
+    auto Z = ilqr_solver_.GetTrajectory();
+    if (!Z) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
+    core_->Upload(*Z);
+    core_->Run(detail::DeviceSolver::kSolveAL);
+    core_->Download(Z.get());
+    core_->Pull();
+  }
+  void UpdateDuals() { core_->Run(detail::DeviceSolver::kUpdateDuals); }
+  void UpdatePenalties() { core_->Run(detail::DeviceSolver::kUpdatePenalties); }
+  double MaxViolation() {
+    core_->Run(detail::DeviceSolver::kCost);
+    return core_->Pull().viol[0];
+  }
+  double GetMaxViolation() { return MaxViolation(); }
+
+ private:
+  std::shared_ptr<detail::DeviceSolver> core_;
+  ilqr::iLQR<n, m> ilqr_solver_;
+};
+
+// The batch axis replaces the reference's thread pool (SolverOptions::nthreads): instance b
+// starts from initial state x0[b] and the controls of the trajectory given to SetTrajectory.
+template <int n, int m>
+class BatchedAugmentedLagrangianiLQR {
+ public:
+  BatchedAugmentedLagrangianiLQR(const problem::Problem& prob, int batch, int device = 0)
+      : core_(std::make_shared<detail::DeviceSolver>(prob, prob.GetDynamics(0)->StateDimension(),
+                                                     prob.GetDynamics(0)->ControlDimension(), true, batch, device)) {}
+
+  int Batch() const { return core_->Batch(); }
+  SolverOptions& GetOptions() { return core_->GetOptions(); }
+  void SetPenalty(double rho) { core_->SetPenalty(rho); }
+  void SetInitialStates(const std::vector<VectorXd>& x0) { core_->SetInitialStates(x0); }
+  void SetTrajectory(std::shared_ptr<Trajectory<n, m>> nominal) {
+    Z_ = std::move(nominal);
+    core_->SetStep(Z_->GetStep(0));
+  }
+  void Solve() {
+    if (!Z_) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
+    core_->Upload(*Z_);
+    core_->Run(detail::DeviceSolver::kSolveAL);
+    core_->Fetch();
+    core_->Pull();
+  }
+  SolverStatus GetStatus(int b) const { return static_cast<SolverStatus>(core_->Last().status.at(b)); }
+  int GetIterations(int b) const { return core_->Last().iters.at(static_cast<size_t>(b) * 3 + 2); }
+  int GetOuterIterations(int b) const { return core_->Last().iters.at(static_cast<size_t>(b) * 3 + 1); }
+  double GetCost(int b) const { return core_->Last().cost.at(b); }
+  double GetMaxViolation(int b) const { return core_->Last().viol.at(b); }
+  Trajectory<n, m> GetTrajectory(int b) const {
+    Trajectory<n, m> Z = *Z_;
+    core_->CopyOut(&Z, b);
+    return Z;
+  }
+  int64_t KernelLaunches() const { return core_->KernelLaunches(); }
+
+ private:
+  std::shared_ptr<detail::DeviceSolver> core_;
+  std::shared_ptr<Trajectory<n, m>> Z_;
+};
+
+}  // namespace augmented_lagrangian
+}  // namespace altro

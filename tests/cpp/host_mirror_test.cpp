@@ -1,0 +1,219 @@
+// Reference-style tests written against the host mirror (altro_cpp_b200/host): they read like
+// test/ilqr/unicycle_ilqr_test.cpp, test/augmented_lagrangian/auglag_test.cpp and
+// test/examples/example_*_test.cpp of the reference and expect the same golden numbers, but every
+// solver method runs on the device.
+//
+//   host_mirror_test cpu   checks that need no GPU (descriptor plumbing, loud failure)
+//   host_mirror_test gpu   everything
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "examples/problems/triple_integrator.hpp"
+#include "examples/problems/unicycle.hpp"
+
+namespace {
+
+int failures = 0;
+#define EXPECT(cond)                                                          \
+  do {                                                                        \
+    if (!(cond)) {                                                            \
+      std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond);             \
+      ++failures;                                                             \
+    }                                                                         \
+  } while (0)
+
+using altro::SolverStatus;
+using altro::problems::TripleIntegratorProblem;
+using altro::problems::UnicycleProblem;
+
+// a user-defined model without a device descriptor: the reference would call its virtual
+// Evaluate on the host; here the solver must refuse it
+class HostOnlyModel : public altro::problem::ContinuousDynamics {
+ public:
+  int StateDimension() const override { return 3; }
+  int ControlDimension() const override { return 2; }
+};
+
+void TestDescriptors() {
+  UnicycleProblem def;
+  def.SetScenario(UnicycleProblem::kThreeObstacles);
+  altro::problem::Problem prob = def.MakeProblem(true);
+  EXPECT(prob.IsFullyDefined());
+  EXPECT(prob.NumSegments() == 100);
+  EXPECT(prob.NumConstraints(0) == 4);    // control bounds only
+  EXPECT(prob.NumConstraints(1) == 7);    // 3 circles + 4 bound rows
+  EXPECT(prob.NumConstraints(100) == 3);  // goal
+  EXPECT(def.GetTimeStep() == 5.0f / 100);
+
+  altro::device::ConstraintDesc d;
+  EXPECT(prob.GetInequalityConstraints()[1][0]->Describe(&d));
+  EXPECT(d.kind == altro::device::ConstraintDesc::kCircle && d.a.size() == 3 && d.c[0] == 0.425);
+  altro::device::CostDesc c;
+  EXPECT(prob.GetCostFunction(100)->Describe(&c));
+  EXPECT(c.Q[0] == 10.0 && c.q[0] == -30.0 && c.R[0] == 0.0);
+
+  // ControlBound drops infinite rows (basic_constraints.hpp:136-143 there)
+  altro::examples::ControlBound half(2);
+  half.SetUpperBound({1.0, 2.0});
+  EXPECT(half.OutputDimension() == 2);
+  bool threw = false;
+  try {
+    altro::examples::ControlBound bad({1.0}, {0.0});
+  } catch (const std::invalid_argument&) {
+    threw = true;
+  }
+  EXPECT(threw);
+
+  // a functor that cannot be described is rejected before any device work
+  altro::problem::Problem custom(10);
+  auto model = std::make_shared<altro::problem::DiscretizedModel<HostOnlyModel>>(HostOnlyModel());
+  auto cost = std::make_shared<altro::examples::QuadraticCost>(altro::examples::QuadraticCost::LQRCost(
+      altro::MatrixXd::Identity(3, 3), altro::MatrixXd::Identity(2, 2), altro::VectorXd::Zero(3),
+      altro::VectorXd::Zero(2)));
+  for (int k = 0; k <= 10; ++k) custom.SetCostFunction(cost, k);
+  for (int k = 0; k < 10; ++k) custom.SetDynamics(model, k);
+  custom.SetInitialState(altro::VectorXd::Zero(3));
+  altro::ilqr::iLQR<3, 2> solver(custom);
+  auto Z = std::make_shared<altro::Trajectory<3, 2>>(3, 2, 10);
+  Z->SetUniformStep(0.1f);
+  int code = 0;
+  try {
+    solver.SetTrajectory(Z);
+  } catch (const altro::DeviceError& e) {
+    code = e.code;
+  }
+  EXPECT(code == ALTRO_B200_ERR_UNSUPPORTED);
+}
+
+// without a GPU every solver reports the CUDA error instead of computing on the host
+void TestNoDeviceIsLoud() {
+  UnicycleProblem def;
+  int code = 0;
+  std::string what;
+  try {
+    auto solver = def.MakeSolver();
+  } catch (const altro::DeviceError& e) {
+    code = e.code;
+    what = e.what();
+  }
+  EXPECT(code == ALTRO_B200_ERR_CUDA);
+  EXPECT(what.find("no CPU fallback") != std::string::npos);
+}
+
+// test/ilqr/unicycle_ilqr_test.cpp:28-100
+void TestUnicycleILQR() {
+  UnicycleProblem def;
+  auto solver = def.MakeSolver();
+  const double J0 = solver.Cost();
+  EXPECT(std::fabs(J0 - 259.27636137767087) < 1e-5);
+  solver.UpdateExpansions();
+  solver.BackwardPass();
+  solver.ForwardPass();
+  EXPECT(solver.Cost() < J0);
+
+  auto fresh = def.MakeSolver();
+  fresh.Solve();
+  EXPECT(fresh.GetStatus() == SolverStatus::kSolved);
+  EXPECT(fresh.GetStats().iterations_inner == 9);
+  EXPECT(std::fabs(fresh.Cost() - 0.0387016567) < 1e-5);
+  const altro::VectorXd& xN = fresh.GetTrajectory()->State(def.N);
+  EXPECT(std::fabs(xN(0) - 1.5) < 1e-2 && std::fabs(xN(1) - 1.5) < 1e-2);
+  auto g = fresh.GetKnotPointFunction(0);
+  EXPECT(g.GetFeedbackGain().rows() == 2 && g.GetFeedbackGain().cols() == 3);
+}
+
+// test/augmented_lagrangian/auglag_test.cpp:326-380
+void TestUnicycleAugLag() {
+  UnicycleProblem def;
+  auto solver = def.MakeALSolver();
+  solver.GetOptions().constraint_tolerance = 1e-6;
+  for (int repeat = 0; repeat < 2; ++repeat) {
+    *solver.GetiLQRSolver().GetTrajectory() = def.InitialTrajectory();
+    solver.Solve();
+    EXPECT(solver.GetStatus() == SolverStatus::kSolved);
+    EXPECT(solver.GetStats().iterations_total == 14);
+    EXPECT(solver.GetStats().iterations_outer == 5);
+    EXPECT(solver.MaxViolation() < 1e-6);
+    const double J = solver.GetiLQRSolver().Cost();
+    EXPECT(std::fabs(J - 0.03893465058924039) / 0.03893465058924039 < 1e-9);
+  }
+}
+
+// test/examples/example_unicycle_test.cpp:69-89 (BASELINE config C1)
+void TestThreeObstacles() {
+  UnicycleProblem def;
+  def.SetScenario(UnicycleProblem::kThreeObstacles);
+  altro::augmented_lagrangian::AugmentedLagrangianiLQR<3, 2> solver(def.MakeProblem(true));
+  auto Z = std::make_shared<altro::Trajectory<3, 2>>(def.InitialTrajectory());
+  solver.SetTrajectory(Z);
+  solver.SetPenalty(10.0);
+  solver.Solve();
+  EXPECT(solver.GetStatus() == SolverStatus::kSolved);
+  EXPECT(solver.GetStats().iterations_total == 50);
+  EXPECT(solver.GetStats().iterations_outer == 5);
+  EXPECT(solver.MaxViolation() < 1e-4);
+  for (int i = 0; i < 3; ++i) {
+    altro::examples::Circle c(def.cx(i), def.cy(i), def.cr(i));
+    for (int k = 0; k <= def.N; ++k) EXPECT(c.Distance(Z->State(k)(0), Z->State(k)(1)) > -1e-3);
+  }
+  for (int i = 0; i < 3; ++i) EXPECT(std::fabs(Z->State(def.N)(i) - def.xf(i)) < 1e-4);
+
+  // the batched solver gives the nominal instance the same answer
+  altro::augmented_lagrangian::BatchedAugmentedLagrangianiLQR<3, 2> batched(def.MakeProblem(true), 64);
+  batched.SetTrajectory(std::make_shared<altro::Trajectory<3, 2>>(def.InitialTrajectory()));
+  std::vector<altro::VectorXd> x0(64, def.x0);
+  for (int b = 1; b < 64; ++b) x0[b](1) += 0.002 * b;
+  batched.SetInitialStates(x0);
+  batched.SetPenalty(10.0);
+  batched.Solve();
+  EXPECT(batched.GetStatus(0) == SolverStatus::kSolved);
+  EXPECT(batched.GetIterations(0) == 50 && batched.GetOuterIterations(0) == 5);
+  altro::Trajectory<3, 2> Z0 = batched.GetTrajectory(0);
+  double diff = 0.0;
+  for (int k = 0; k <= def.N; ++k)
+    for (int i = 0; i < 3; ++i) diff = std::fmax(diff, std::fabs(Z0.State(k)(i) - Z->State(k)(i)));
+  EXPECT(diff == 0.0);
+  EXPECT(batched.KernelLaunches() > 0);
+}
+
+// test/ilqr/ilqr_test.cpp:304-336, test/examples/example_triple_integrator_test.cpp:16-70
+void TestTripleIntegrator() {
+  TripleIntegratorProblem def;
+  auto solver = def.MakeSolver();
+  solver.Solve();
+  EXPECT(solver.GetStatus() == SolverStatus::kSolved);
+  EXPECT(solver.GetStats().iterations_inner == 2);
+
+  auto al = def.MakeALSolver();
+  al.Solve();
+  EXPECT(al.GetStatus() == SolverStatus::kSolved);
+  EXPECT(al.MaxViolation() < 1e-4);
+  auto Z = al.GetiLQRSolver().GetTrajectory();
+  for (int i = 0; i < 6; ++i) EXPECT(std::fabs(Z->State(10)(i) - def.xf(i)) < 1e-4);
+  EXPECT(std::fabs(Z->Control(0)(0) - 100.0) < 1e-4 && std::fabs(Z->Control(0)(1) - 200.0) < 1e-4);
+}
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+  const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
+  try {
+    TestDescriptors();
+    if (!gpu) {
+      TestNoDeviceIsLoud();
+    } else {
+      TestUnicycleILQR();
+      TestUnicycleAugLag();
+      TestThreeObstacles();
+      TestTripleIntegrator();
+    }
+  } catch (const std::exception& e) {
+    std::printf("FAIL unexpected exception: %s\n", e.what());
+    return 3;
+  }
+  std::printf("%s: %d failure(s)\n", gpu ? "gpu" : "cpu", failures);
+  return failures ? 1 : 0;
+}

@@ -1,0 +1,92 @@
+"""The host mirror of the reference's C++ API (altro_cpp_b200/host): reference-style programs
+compile against it, refuse to run without a GPU and reproduce the reference's golden numbers on
+one (tests/cpp/host_mirror_test.cpp)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+import altro_cpp_b200 as pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "altro_cpp_b200")
+HOST = os.path.join(LIBDIR, "host")
+
+
+def compile_program(tmp_path, src, name):
+    pkg.lib()  # makes sure libaltro_b200.so exists
+    exe = str(tmp_path / name)
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
+                           "-I", os.path.join(ROOT, "include"), "-I", HOST, src, "-o", exe,
+                           "-L", LIBDIR, "-laltro_b200", f"-Wl,-rpath,{LIBDIR}"])
+    return exe
+
+
+def has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_host_mirror_cpu_checks_and_loud_failure(tmp_path):
+    exe = compile_program(tmp_path, os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp"), "host_mirror_test")
+    if has_gpu():
+        pytest.skip("a GPU is present: covered by the gpu test")
+    r = subprocess.run([exe, "cpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "cpu: 0 failure(s)" in r.stdout
+
+
+def test_benchmark_programs_refuse_to_run_without_gpu(tmp_path):
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    for name in ("benchmark_unicycle", "benchmark_triple_integrator"):
+        exe = compile_program(tmp_path, os.path.join(HOST, "perf", name + ".cpp"), name)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 2
+        assert "no usable CUDA device" in r.stderr
+
+
+@pytest.mark.skipif(shutil.which("cmake") is None, reason="cmake not installed")
+def test_cmake_project_with_reference_target_names(tmp_path):
+    pkg.lib()
+    build = str(tmp_path / "build")
+    subprocess.check_call(["cmake", "-S", ROOT, "-B", build, "-DALTRO_B200_PREBUILT=ON"],
+                          stdout=subprocess.DEVNULL)
+    subprocess.check_call(["cmake", "--build", build, "-j", "4"], stdout=subprocess.DEVNULL)
+    for exe in ("benchmark_unicycle", "benchmark_triple_integrator", "host_mirror_test"):
+        assert os.path.exists(os.path.join(build, exe))
+    # a downstream project that links the reference's target name
+    down = tmp_path / "downstream"
+    down.mkdir()
+    (down / "CMakeLists.txt").write_text(
+        "cmake_minimum_required(VERSION 3.18)\nproject(Down LANGUAGES CXX)\n"
+        f"set(ALTRO_B200_PREBUILT ON CACHE BOOL \"\")\nset(ALTRO_BUILD_TESTS OFF CACHE BOOL \"\")\n"
+        f"set(ALTRO_BUILD_BENCHMARKS OFF CACHE BOOL \"\")\n"
+        f"add_subdirectory({ROOT} altro)\nadd_executable(app app.cpp)\n"
+        "target_link_libraries(app PRIVATE altro::altro)\n")
+    (down / "app.cpp").write_text(
+        '#include "altro/augmented_lagrangian/al_solver.hpp"\n#include "examples/problems/unicycle.hpp"\n'
+        "int main() { altro::problems::UnicycleProblem p; return p.MakeProblem().NumSegments() == 100 ? 0 : 1; }\n")
+    subprocess.check_call(["cmake", "-S", str(down), "-B", str(down / "b")], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["cmake", "--build", str(down / "b")], stdout=subprocess.DEVNULL)
+    assert subprocess.run([str(down / "b" / "app")]).returncode == 0
+
+
+@pytest.mark.gpu
+def test_host_mirror_reproduces_reference_goldens_on_device(tmp_path):
+    exe = compile_program(tmp_path, os.path.join(ROOT, "tests", "cpp", "host_mirror_test.cpp"), "host_mirror_test")
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "gpu: 0 failure(s)" in r.stdout
+
+
+@pytest.mark.gpu
+def test_benchmark_unicycle_single_and_batched(tmp_path):
+    exe = compile_program(tmp_path, os.path.join(HOST, "perf", "benchmark_unicycle.cpp"), "benchmark_unicycle")
+    r = subprocess.run([exe, "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("iters = 50, outer = 5, status = 0") == 2
+    r = subprocess.run([exe, "2", "512"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("nominal iters = 50") == 2
