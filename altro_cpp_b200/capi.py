@@ -247,6 +247,15 @@ class BatchSolver:
             self._call("get_duals_host", ctypes.c_int(k), _p(lam), ctypes.byref(p), _stream_ptr(stream))
         return lam[:, :p.value]
 
+    def constraint_values(self, k, stream=None):
+        """c(x_k, u_k) of the current trajectory, ALCost row order -> [B][p_k]."""
+        pmax, pk = ctypes.c_int(0), ctypes.c_int(0)
+        self._call("get_duals_host", ctypes.c_int(k), ctypes.cast(None, _dp), ctypes.byref(pmax), _stream_ptr(stream))
+        c = np.zeros((self.B, max(pmax.value, 1)))
+        self._call("get_constraint_values_host", ctypes.c_int(k), _p(c) if pmax.value else ctypes.cast(None, _dp),
+                   ctypes.byref(pk), _stream_ptr(stream))
+        return c[:, :pk.value]
+
     def results(self, stream=None):
         out = self.alloc_outputs(want_traj=False)
         self._call("get_results_host", _p(out["cost"]), _p(out["viol"]), out["status"].ctypes.data_as(_ip),

@@ -147,6 +147,7 @@ struct Ops {
   cudaError_t (*phase)(const SolverParams&, int phase, cudaStream_t);
   cudaError_t (*expansions)(const SolverParams&, cudaStream_t);
   cudaError_t (*backward_mat)(const SolverParams&, bool store_ctg, cudaStream_t);
+  cudaError_t (*con_values)(const SolverParams&, int k, double* out, cudaStream_t);
   bool large = false;  // one instance per CTA (large.cuh): whole solves only, W = 1 layout
 };
 
@@ -179,6 +180,10 @@ Ops make_ops() {
     k_update_expansions<M, W><<<grid, 128, P.blob_bytes, st>>>(P);
     return cudaGetLastError();
   };
+  o.con_values = [](const SolverParams& P, int k, double* out, cudaStream_t st) -> cudaError_t {
+    k_constraint_values<M, W><<<(P.B + 127) / 128, 128, P.blob_bytes, st>>>(P, k, out);
+    return cudaGetLastError();
+  };
   o.backward_mat = [](const SolverParams& P, bool store_ctg, cudaStream_t st) -> cudaError_t {
     const int smem = kBpStages * Lane<M, W>::nexp * kWarp * sizeof(double) + kBpStages * 8;
     const int grid = (P.T + kWarp / W - 1) / (kWarp / W);
@@ -205,6 +210,7 @@ Ops make_large_ops_32_8() {
   o.phase = nullptr;
   o.expansions = nullptr;
   o.backward_mat = nullptr;
+  o.con_values = nullptr;
   o.solve = [](const SolverParams& P, int mode, int, cudaStream_t st) -> cudaError_t {
     return altro_b200_launch_solve_large_32_8(P, mode, st);
   };
@@ -273,6 +279,7 @@ struct altro_b200_solver {
   std::vector<void*> allocs;
   bool inputs_set = false;
   int model = 0, sm_count = 148;
+  std::vector<int> p_knot;  // constraint rows per knot (ALCost order)
   // secondary workspaces: unfinished instances are re-packed into them between k_solve launches
   struct Secondary {
     SolverParams P;
@@ -586,6 +593,12 @@ int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_con
   s->T = (batch + s->W - 1) / s->W;
   s->Bp = s->T * s->W;
   s->pmax = pmax;
+  s->p_knot.assign(p->N + 1, 0);
+  if (use_constraints)
+    for (int k = 0; k <= p->N; ++k) {
+      for (const ConBlock& b : p->eq[k]) s->p_knot[k] += b.p;
+      for (const ConBlock& b : p->ineq[k]) s->p_knot[k] += b.p;
+    }
   s->device = device;
   s->use_al = use_constraints != 0;
   lookup_ops(p->n, p->m, p->model, s->W, &s->ops);
@@ -964,6 +977,24 @@ int altro_b200_get_duals_host(altro_b200_solver* s, int k, double* lambda, int* 
   if (p_out) *p_out = s->pmax;
   if (lambda && s->pmax > 0)
     return unpack_to(s, s->P.LAM, s->N + 1, s->pmax, 0, s->pmax, k, 1, lambda, true, false, S(stream));
+  return 0;
+}
+int altro_b200_get_constraint_values_host(altro_b200_solver* s, int k, double* c, int* p_out, void* stream) {
+  if (!s || k < 0 || k > s->N) return fail(ALTRO_B200_ERR_ARG, "get_constraint_values: bad argument");
+  if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
+  if (p_out) *p_out = s->p_knot[k];
+  if (!c || s->pmax == 0) return 0;
+  if (!s->ops.con_values)
+    return fail(ALTRO_B200_ERR_UNSUPPORTED, "constraint values are not available on the large-state path");
+  DeviceGuard guard(s->device);
+  const size_t bytes = static_cast<size_t>(s->B) * s->pmax * sizeof(double);
+  int rc = s->ensure_io(bytes);
+  if (rc) return rc;
+  cudaError_t e = s->ops.con_values(s->P, k, s->d_io, S(stream));
+  s->launches += 1;
+  if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("k_constraint_values launch: ") + cudaGetErrorString(e));
+  CU(cudaMemcpyAsync(c, s->d_io, bytes, cudaMemcpyDeviceToHost, S(stream)));
+  CU(cudaStreamSynchronize(S(stream)));
   return 0;
 }
 int altro_b200_get_results_host(altro_b200_solver* s, double* cost, double* viol, int32_t* status,

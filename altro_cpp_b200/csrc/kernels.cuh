@@ -1065,6 +1065,33 @@ __global__ void __launch_bounds__(128) k_update_expansions(SolverParams P) {
   if (k == 0) L.sc(S_CSRC_ALPHA) = -1.0;
 }
 
+// Constraint values c(x_k, u_k) of the current trajectory at one knot, rows in ALCost order
+// (what ConstraintValues::GetConstraintValue() holds after Cost(), constraint_values.hpp:216-221;
+// used by GetConstraintInfo / PrintViolations, al_solver.hpp:68-104).  out = [B][pmax], rows past
+// the knot's own count are zero.
+template <class M, int W>
+__global__ void __launch_bounds__(128) k_constraint_values(SolverParams P, int k, double* out) {
+  extern __shared__ __align__(128) char s_blob[];
+  copy_blob(P.blob, s_blob, P.blob_bytes);
+  constexpr int n = M::n, m = M::m;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const Lane<M, W> L(P, s_blob, b / W, b % W);
+  const double* zc = L.z(L.is(I_ZSEL), k);
+  double x[n], u[m];
+  ALTRO_UNROLL
+  for (int q = 0; q < n; ++q) x[q] = zc[q * W];
+  ALTRO_UNROLL
+  for (int q = 0; q < m; ++q) u[q] = zc[(n + q) * W];
+  const ConSet& cs = L.D.conset(k);
+  double* o = out + static_cast<size_t>(b) * P.pmax;
+  for (int r = 0; r < P.pmax; ++r) o[r] = 0.0;
+  for (int bi = 0; bi < cs.nblocks; ++bi) {
+    const ConBlock& blk = cs.blk[bi];
+    for (int i = 0; i < blk.p; ++i) o[blk.row0 + i] = con_row_fast<n, m>(blk, i, x, u);
+  }
+}
+
 // --- TMA 1-D bulk copy + mbarrier helpers (cp.async.bulk -> SASS UBLKCP) -------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

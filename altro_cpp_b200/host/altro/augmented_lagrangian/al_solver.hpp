@@ -10,6 +10,9 @@
 //   MaxViolation()                :417     altro_b200_get_results_host (viol)
 #pragma once
 
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -52,8 +55,59 @@ class AugmentedLagrangianiLQR {
     return core_->Pull().viol[0];
   }
   double GetMaxViolation() { return MaxViolation(); }
+  double GetMaxPenalty() { return core_->MaxPenalty(0); }
+  int NumConstraints(int k) const { return core_->GetProblem().NumConstraints(k); }
+  int NumConstraints() const { return core_->GetProblem().NumConstraints(); }
+  // dual variables of knot k, equalities then inequalities (GetALCost(k)->...->GetDuals() there)
+  VectorXd GetDuals(int k) {
+    const std::vector<double> lam = core_->Duals(k, 0);
+    VectorXd out(static_cast<int>(lam.size()));
+    for (int i = 0; i < out.size(); ++i) out(i) = lam[i];
+    return out;
+  }
+
+  // al_solver.hpp:85-104 there: one entry per constraint and knot point with its violation
+  // c - Pi_K(c) of the current trajectory, optionally sorted by its infinity norm
+  std::vector<constraints::ConstraintInfo> GetConstraintInfo(bool should_sort = false) {
+    const problem::Problem& prob = core_->GetProblem();
+    std::vector<constraints::ConstraintInfo> coninfo;
+    for (int k = 0; k <= NumSegments(); ++k) {
+      if (prob.NumConstraints(k) == 0) continue;
+      const std::vector<double> c = core_->ConstraintValues(k, 0);
+      int row = 0;
+      for (const auto& con : prob.GetEqualityConstraints()[k]) {
+        constraints::ConstraintInfo info{con->GetLabel(), k, VectorXd(con->OutputDimension()), con->GetConstraintType()};
+        for (int i = 0; i < info.violation.size(); ++i) info.violation(i) = c.at(row++);
+        coninfo.push_back(info);
+      }
+      for (const auto& con : prob.GetInequalityConstraints()[k]) {
+        constraints::ConstraintInfo info{con->GetLabel(), k, VectorXd(con->OutputDimension()), con->GetConstraintType()};
+        for (int i = 0; i < info.violation.size(); ++i) {
+          const double ci = c.at(row++);
+          info.violation(i) = ci > 0.0 ? ci : 0.0;
+        }
+        coninfo.push_back(info);
+      }
+    }
+    if (should_sort)
+      std::stable_sort(coninfo.begin(), coninfo.end(),
+                       [](const constraints::ConstraintInfo& a, const constraints::ConstraintInfo& b) {
+                         return InfNorm(a.violation) > InfNorm(b.violation);
+                       });
+    return coninfo;
+  }
+  void PrintViolations(bool should_sort = false, int precision = 4) {
+    const std::vector<constraints::ConstraintInfo> coninfo = GetConstraintInfo(should_sort);
+    std::printf("Got %d constraints\n", static_cast<int>(coninfo.size()));
+    for (const constraints::ConstraintInfo& info : coninfo) std::printf("%s\n", info.ToString(precision).c_str());
+  }
 
  private:
+  static double InfNorm(const VectorXd& v) {
+    double r = 0.0;
+    for (int i = 0; i < v.size(); ++i) r = std::fabs(v(i)) > r ? std::fabs(v(i)) : r;
+    return r;
+  }
   std::shared_ptr<detail::DeviceSolver> core_;
   ilqr::iLQR<n, m> ilqr_solver_;
 };

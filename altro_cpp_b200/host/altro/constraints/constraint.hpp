@@ -4,7 +4,9 @@
 #pragma once
 
 #include <memory>
+#include <sstream>
 #include <string>
+#include <type_traits>
 
 #include "altro/device_descriptor.hpp"
 #include "altro/eigentypes.hpp"
@@ -17,13 +19,32 @@ class NegativeOrthant {};
 using Equality = ZeroCone;
 using Inequality = NegativeOrthant;
 
+// One entry of AugmentedLagrangianiLQR::GetConstraintInfo() (constraint.hpp:134-141 there)
+struct ConstraintInfo {
+  std::string label;
+  int index;           // knot point
+  VectorXd violation;  // c - Pi_K(c)
+  std::string type;
+  std::string ToString(int precision = 4) const {
+    std::ostringstream os;
+    os << label << " at index " << index << ": [";
+    os.precision(precision);
+    for (int i = 0; i < violation.size(); ++i) os << (i ? ", " : "") << violation(i);
+    os << "]";
+    return os.str();
+  }
+};
+
 template <class ConType>
 class Constraint {
  public:
   using ConstraintType = ConType;
   virtual ~Constraint() = default;
   virtual int OutputDimension() const = 0;
-  virtual std::string GetLabel() const { return "Constraint"; }
+  virtual std::string GetLabel() const { return GetConstraintType(); }
+  std::string GetConstraintType() const {
+    return std::is_same<ConType, Equality>::value ? "Equality Constraint" : "Inequality Constraint";
+  }
   virtual bool Describe(device::ConstraintDesc*) const { return false; }
 };
 

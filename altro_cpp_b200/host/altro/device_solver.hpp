@@ -205,6 +205,64 @@ class DeviceSolver {
       for (int i = 0; i < n_; ++i) (*P)(i, j) = Pall[static_cast<size_t>(b) * n_ * n_ + j * n_ + i];
     for (int i = 0; i < n_; ++i) (*p)(i) = pall[static_cast<size_t>(b) * n_ + i];
   }
+  // c(x_k, u_k) of instance b at knot k, ALCost row order (equalities, then inequalities)
+  std::vector<double> ConstraintValues(int k, int b) {
+    Need();
+    int pmax = 0, pk = 0;
+    Check(altro_b200_get_duals_host(solver_, k, nullptr, &pmax, nullptr), "GetConstraintInfo");
+    std::vector<double> all(static_cast<size_t>(B_) * (pmax > 0 ? pmax : 1));
+    Check(altro_b200_get_constraint_values_host(solver_, k, pmax > 0 ? all.data() : nullptr, &pk, nullptr),
+          "GetConstraintInfo");
+    return std::vector<double>(all.begin() + static_cast<size_t>(b) * pmax,
+                               all.begin() + static_cast<size_t>(b) * pmax + pk);
+  }
+  std::vector<double> Duals(int k, int b) {
+    Need();
+    int pmax = 0, pk = 0;
+    Check(altro_b200_get_duals_host(solver_, k, nullptr, &pmax, nullptr), "GetDuals");
+    Check(altro_b200_get_constraint_values_host(solver_, k, nullptr, &pk, nullptr), "GetDuals");
+    std::vector<double> all(static_cast<size_t>(B_) * (pmax > 0 ? pmax : 1));
+    if (pmax > 0) Check(altro_b200_get_duals_host(solver_, k, all.data(), &pmax, nullptr), "GetDuals");
+    return std::vector<double>(all.begin() + static_cast<size_t>(b) * pmax,
+                               all.begin() + static_cast<size_t>(b) * pmax + pk);
+  }
+  double MaxPenalty(int b = 0) {
+    Need();
+    std::vector<double> pen(B_);
+    Check(altro_b200_get_scalars_host(solver_, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                      pen.data(), nullptr, nullptr),
+          "GetMaxPenalty");
+    return pen[b];
+  }
+  void Expansion(int k, int b, MatrixXd* A, MatrixXd* Bm, MatrixXd* lxx, MatrixXd* lxu, MatrixXd* luu, VectorXd* lx,
+                 VectorXd* lu) {
+    Need();
+    const size_t B = B_;
+    std::vector<double> a(B * n_ * n_), bb(B * n_ * m_), xx(B * n_ * n_), xu(B * n_ * m_), uu(B * m_ * m_), x(B * n_),
+        u(B * m_);
+    Check(altro_b200_get_expansion_host(solver_, k, a.data(), bb.data(), xx.data(), xu.data(), uu.data(), x.data(),
+                                        u.data(), nullptr),
+          "GetCostExpansion");
+    auto mat = [&](const std::vector<double>& v, int r, int c) {
+      MatrixXd M(r, c);
+      for (int j = 0; j < c; ++j)
+        for (int i = 0; i < r; ++i) M(i, j) = v[static_cast<size_t>(b) * r * c + j * r + i];
+      return M;
+    };
+    auto vec = [&](const std::vector<double>& v, int r) {
+      VectorXd V(r);
+      for (int i = 0; i < r; ++i) V(i) = v[static_cast<size_t>(b) * r + i];
+      return V;
+    };
+    *A = mat(a, n_, n_);
+    *Bm = mat(bb, n_, m_);
+    *lxx = mat(xx, n_, n_);
+    *lxu = mat(xu, n_, m_);
+    *luu = mat(uu, m_, m_);
+    *lx = vec(x, n_);
+    *lu = vec(u, m_);
+  }
+  const problem::Problem& GetProblem() const { return prob_; }
   int64_t KernelLaunches() const { return solver_ ? altro_b200_kernel_launches(solver_) : 0; }
 
  private:

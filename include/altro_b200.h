@@ -215,6 +215,12 @@ int altro_b200_get_expansion_host(altro_b200_solver* s, int k, double* A, double
 /* duals of knot k, ALCost order -> lambda [B][p]; returns p via *p_out */
 int altro_b200_get_duals_host(altro_b200_solver* s, int k, double* lambda, int* p_out,
                               void* stream);
+/* Constraint values c(x_k, u_k) of the current trajectory at knot k, ALCost row order -> c [B][pmax]
+ * (pmax = the row count returned by altro_b200_get_duals_host; rows past *p_out, the knot's own
+ * count, are zero).  What GetALCost(k)->...->GetConstraintValue() holds after Cost(); feeds
+ * GetConstraintInfo()/PrintViolations() (al_solver.hpp:68-104, constraint_values.hpp:216-221). */
+int altro_b200_get_constraint_values_host(altro_b200_solver* s, int k, double* c, int* p_out,
+                                          void* stream);
 /* Per-instance results of the last solve / phase:
  *   cost   [B]   Cost() of the current trajectory under the current duals/penalties
  *   viol   [B]   GetMaxViolation() (al_solver.hpp:417-422)

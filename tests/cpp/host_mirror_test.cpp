@@ -114,6 +114,35 @@ void TestUnicycleILQR() {
   solver.ForwardPass();
   EXPECT(solver.Cost() < J0);
 
+  // unicycle_ilqr_test.cpp:40-54: cost-to-go gradient and feedforward gain at knot 0
+  auto step = def.MakeSolver();
+  step.UpdateExpansions();
+  step.BackwardPass();
+  auto kpf = step.GetKnotPointFunction(0, true);
+  const double p0[3] = {0.024904637422419617, -0.46496022574032614, -0.0573096310550007};
+  const double d0[2] = {-2.565783457444465, 5.514158930898376};
+  for (int i = 0; i < 3; ++i) EXPECT(std::fabs(kpf.GetCostToGoGradient()(i) - p0[i]) < 1e-5 * 0.47);
+  for (int i = 0; i < 2; ++i) EXPECT(std::fabs(kpf.GetFeedforwardGain()(i) - d0[i]) < 1e-5 * 6.1);
+  EXPECT(kpf.GetDynamicsExpansion().GetA().rows() == 3 && kpf.GetDynamicsExpansion().GetB().cols() == 2);
+  EXPECT(kpf.GetDynamicsExpansion().GetA()(0, 0) == 1.0);  // d x_next / d x = 1 for the unicycle
+  EXPECT(kpf.GetCostExpansion().dudu()(0, 0) > 0.0);
+  EXPECT(step.NumThreads() == 1 && step.GetTaskAssignment().back() == def.N + 1);
+
+  // the problem's initial state is shared with the solver (ilqr_class_test.cpp:84-96)
+  {
+    altro::problem::Problem prob = def.MakeProblem();
+    altro::ilqr::iLQR<3, 2> late(def.N);
+    late.InitializeFromProblem(prob);
+    auto Zl = std::make_shared<altro::Trajectory<3, 2>>(def.InitialTrajectory());
+    late.SetTrajectory(Zl);
+    altro::VectorXd moved = prob.GetInitialState();
+    moved(0) = 0.25;
+    prob.SetInitialState(moved);
+    EXPECT((*late.GetInitialState())(0) == 0.25);
+    late.Rollout();
+    EXPECT(Zl->State(0)(0) == 0.25);
+  }
+
   auto fresh = def.MakeSolver();
   fresh.Solve();
   EXPECT(fresh.GetStatus() == SolverStatus::kSolved);
@@ -160,6 +189,26 @@ void TestThreeObstacles() {
     for (int k = 0; k <= def.N; ++k) EXPECT(c.Distance(Z->State(k)(0), Z->State(k)(1)) > -1e-3);
   }
   for (int i = 0; i < 3; ++i) EXPECT(std::fabs(Z->State(def.N)(i) - def.xf(i)) < 1e-4);
+
+  // al_solver.hpp:68-104: one ConstraintInfo per constraint and knot point
+  EXPECT(solver.NumConstraints() == 4 * 100 + 3 * 99 + 3);
+  EXPECT(solver.NumConstraints(1) == 7);
+  auto coninfo = solver.GetConstraintInfo();
+  EXPECT(coninfo.size() == 100 + 99 + 1);
+  EXPECT(coninfo.front().index == 0 && coninfo.front().label == "Control Bound");
+  EXPECT(coninfo[1].label == "Circle Constraint" && coninfo[1].index == 1 && coninfo[1].violation.size() == 3);
+  EXPECT(coninfo.back().label == "Goal Constraint" && coninfo.back().type == "Equality Constraint");
+  double worst = 0.0;
+  for (const auto& info : coninfo)
+    for (int i = 0; i < info.violation.size(); ++i) worst = std::fmax(worst, std::fabs(info.violation(i)));
+  EXPECT(std::fabs(worst - solver.MaxViolation()) < 1e-15);  // two device code sites, FMA contraction may differ
+  auto sorted = solver.GetConstraintInfo(true);
+  double first = 0.0;
+  for (int i = 0; i < sorted.front().violation.size(); ++i) first = std::fmax(first, std::fabs(sorted.front().violation(i)));
+  EXPECT(std::fabs(first - worst) < 1e-15);
+  EXPECT(sorted.front().ToString().find(" at index ") != std::string::npos);
+  EXPECT(solver.GetMaxPenalty() >= 1.0 && solver.GetMaxPenalty() <= 1e8);
+  EXPECT(solver.GetDuals(def.N).size() == 3 && solver.GetDuals(0).size() == 4);
 
   // the batched solver gives the nominal instance the same answer
   altro::augmented_lagrangian::BatchedAugmentedLagrangianiLQR<3, 2> batched(def.MakeProblem(true), 64);

@@ -519,3 +519,47 @@ def test_warm_start_resolve_keeps_duals_and_penalties(gpu, oracle):
         Xo, Uo = ref.trajectory()
         assert close(Xg[b], Xo, 1e-8) and close(Ug[b], Uo, 1e-8)
         assert pen[b] == ref.max_penalty()
+
+
+def test_constraint_values_match_definitions_and_max_violation(gpu):
+    """GetConstraintInfo()/PrintViolations() inputs (al_solver.hpp:68-104): the per-knot constraint
+    values of the solved trajectory against the constraint definitions written out in numpy
+    (examples/basic_constraints.hpp:27-36,98-129; obstacle_constraints.hpp:98-120), and their
+    max violation against GetMaxViolation() (constraint_values.hpp:216-221)."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    B = 70
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, B)
+    s.set_inputs(X0)
+    s.solve_al()
+    s.cost()
+    viol = s.results()["viol"]
+    X, U = s.trajectory()
+    cx = cy = np.array([0.25, 0.5, 0.75]) * 3.0
+    lb, ub = np.array([0.0, -3.0]), np.array([3.0, 3.0])
+    worst = np.zeros(B)
+    N = spec.N
+    for k in (0, 1, 50, N - 1, N):
+        c = s.constraint_values(k)
+        if k == N:
+            want = X[:, N] - spec.xf  # goal, equality
+            v = np.abs(want).max(axis=1)
+        else:
+            bound = np.concatenate([lb - U[:, k], U[:, k] - ub], axis=1)
+            if k >= 1:
+                circ = 0.425 ** 2 - ((X[:, k, 0:1] - cx) ** 2 + (X[:, k, 1:2] - cy) ** 2)
+                want = np.concatenate([circ, bound], axis=1)  # circles were added first (unicycle.cpp:52-60)
+            else:
+                want = bound
+            v = np.maximum(want, 0.0).max(axis=1)
+        assert c.shape == want.shape
+        np.testing.assert_allclose(c, want, rtol=1e-13, atol=1e-14)
+    for k in range(N + 1):
+        c = s.constraint_values(k)
+        v = np.abs(c).max(axis=1) if k == N else np.maximum(c, 0.0).max(axis=1)
+        worst = np.maximum(worst, v)
+    np.testing.assert_allclose(worst, viol, rtol=0, atol=1e-16)
+    # the plain iLQR solver carries no constraints
+    s2 = gpu.BatchSolver(spec, 4, use_constraints=False)
+    s2.set_inputs(X0[:4])
+    assert s2.constraint_values(5).shape == (4, 0)
