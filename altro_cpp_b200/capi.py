@@ -30,7 +30,7 @@ class Options(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "max_iterations_total", "max_iterations_outer", "max_iterations_inner",
         "bp_reg_fail_threshold", "check_forwardpass_bounds", "line_search_max_iterations",
-        "reset_duals", "_pad")] + [(n, ctypes.c_double) for n in (
+        "reset_duals", "skip_repeated_iterations")] + [(n, ctypes.c_double) for n in (
         "cost_tolerance", "gradient_tolerance", "bp_reg_increase_factor", "bp_reg_initial",
         "bp_reg_max", "bp_reg_min", "state_max", "control_max", "line_search_lower_bound",
         "line_search_upper_bound", "line_search_decrease_factor", "constraint_tolerance",
@@ -62,6 +62,9 @@ def lib():
                                                ctypes.POINTER(_vp)]
         L.altro_b200_solver_destroy.argtypes = [_vp]
         L.altro_b200_problem_destroy.argtypes = [_vp]
+        L.altro_b200_set_default_engine.argtypes = [ctypes.c_int]
+        L.altro_b200_set_default_engine.restype = None
+        L.altro_b200_solver_engine.argtypes = [_vp]
         _lib = L
     return _lib
 
@@ -95,6 +98,15 @@ def _stream_ptr(stream) -> _vp:
     if hasattr(stream, "cuda_stream"):
         return _vp(stream.cuda_stream)
     return _vp(int(stream))
+
+
+ENGINES = {"fused": 0, "phased": 1}
+
+
+def set_default_engine(name: Optional[str]):
+    """Engine of solvers created from now on: "fused", "phased" or None (environment variable
+    ALTRO_B200_ENGINE, else the built-in default).  Both engines return the same results."""
+    lib().altro_b200_set_default_engine(-1 if name is None else ENGINES[name])
 
 
 class BatchSolver:
@@ -132,6 +144,11 @@ class BatchSolver:
     def _call(self, name, *args):
         fn = getattr(lib(), "altro_b200_" + name)
         _check(fn(self._h, *args), name)
+
+    @property
+    def engine(self) -> str:
+        e = int(lib().altro_b200_solver_engine(self._h))
+        return {v: k for k, v in ENGINES.items()}.get(e, "?")
 
     # ---- options / inputs -----------------------------------------------------------
     def set_options(self, o: Options):

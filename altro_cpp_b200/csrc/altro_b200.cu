@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "phased.cuh"
 
 // large-state path, compiled in its own translation unit (altro_b200_large.cu) without FMA
 // contraction so that its ill-conditioned LLT decisions match the CPU oracle bit for bit
@@ -93,6 +94,10 @@ int build_blob(const altro_b200_problem& p, bool use_constraints, std::vector<ch
         }
       cs.p_total = row;
       pmax = std::max(pmax, row);
+      for (int bi = 0; bi < cs.nblocks; ++bi) {
+        const ConBlock& c = cs.blk[bi];
+        cs.hdr[bi] = make_int4(c.kind | (c.equality << 8) | (c.p << 16), c.row0, c.nl, c.xi | (c.yi << 8));
+      }
     }
     int id = -1;
     for (size_t i = 0; i < sets.size(); ++i)
@@ -125,8 +130,15 @@ int build_blob(const altro_b200_problem& p, bool use_constraints, std::vector<ch
   out->assign(off, 0);
   char* b = out->data();
   std::memcpy(b, &h, sizeof(h));
-  std::memcpy(b + h.off_cost_id, p.cost_id.data(), sizeof(int) * (N + 1));
-  std::memcpy(b + h.off_conset_id, conset_id.data(), sizeof(int) * (N + 1));
+  {
+    std::vector<int> cost_off(N + 1), conset_off(N + 1);
+    for (int k = 0; k <= N; ++k) {
+      cost_off[k] = h.off_cost + static_cast<int>(sizeof(double)) * cost_stride * p.cost_id[k];
+      conset_off[k] = h.off_conset + static_cast<int>(sizeof(ConSet)) * conset_id[k];
+    }
+    std::memcpy(b + h.off_cost_id, cost_off.data(), sizeof(int) * (N + 1));
+    std::memcpy(b + h.off_conset_id, conset_off.data(), sizeof(int) * (N + 1));
+  }
   std::memcpy(b + h.off_h, p.h.data(), sizeof(float) * (N + 1));
   std::memcpy(b + h.off_t, p.t.data(), sizeof(float) * (N + 1));
   if (!p.params.empty())
@@ -143,15 +155,22 @@ int build_blob(const altro_b200_problem& p, bool use_constraints, std::vector<ch
 // Kernel dispatch per device-capable model
 // ------------------------------------------------------------------------------------------
 struct Ops {
-  cudaError_t (*solve)(const SolverParams&, int mode, int budget, cudaStream_t);
+  cudaError_t (*solve)(const SolverParams&, int mode, int budget, int parts, cudaStream_t);
   cudaError_t (*phase)(const SolverParams&, int phase, cudaStream_t);
   cudaError_t (*expansions)(const SolverParams&, cudaStream_t);
   cudaError_t (*backward_mat)(const SolverParams&, bool store_ctg, cudaStream_t);
   cudaError_t (*con_values)(const SolverParams&, int k, double* out, cudaStream_t);
+  // phased engine (phased.cuh); nullptr when the tile width has no instantiation
+  cudaError_t (*expansions_phased)(const SolverParams&, cudaStream_t) = nullptr;
+  cudaError_t (*backward_phased)(const SolverParams&, cudaStream_t) = nullptr;
+  cudaError_t (*ls_wide)(const SolverParams&, int mode, cudaStream_t) = nullptr;
+  cudaError_t (*ls_deep)(const SolverParams&, int mode, int max_instances, cudaStream_t) = nullptr;
+  cudaError_t (*microbench)(const SolverParams&, double* sink, long long* out, int reps, cudaStream_t) = nullptr;
   bool large = false;  // one instance per CTA (large.cuh): whole solves only, W = 1 layout
 };
 
 constexpr int kBpStages = 4;
+constexpr int kPhasedTile = 8;  // tile width of the phased engine's workspaces
 
 template <class M, int W>
 int solve_smem(const SolverParams& P) {
@@ -161,11 +180,11 @@ int solve_smem(const SolverParams& P) {
 template <class M, int W>
 Ops make_ops() {
   Ops o;
-  o.solve = [](const SolverParams& P, int mode, int budget, cudaStream_t st) -> cudaError_t {
+  o.solve = [](const SolverParams& P, int mode, int budget, int parts, cudaStream_t st) -> cudaError_t {
     const int smem = solve_smem<M, W>(P);
     cudaError_t e = cudaFuncSetAttribute(k_solve<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    k_solve<M, W><<<(P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st>>>(P, mode, budget);
+    k_solve<M, W><<<(P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st>>>(P, mode, budget, parts);
     return cudaGetLastError();
   };
   o.phase = [](const SolverParams& P, int phase, cudaStream_t st) -> cudaError_t {
@@ -201,6 +220,40 @@ Ops make_ops() {
     }
     return cudaGetLastError();
   };
+  if constexpr (W == kPhasedTile) {
+    o.microbench = [](const SolverParams& P, double* sink, long long* out, int reps, cudaStream_t st) -> cudaError_t {
+      k_microbench<M, W><<<1, kWarp, P.blob_bytes, st>>>(P, sink, out, reps);
+      return cudaGetLastError();
+    };
+    o.expansions_phased = [](const SolverParams& P, cudaStream_t st) -> cudaError_t {
+      dim3 grid((P.B + 127) / 128, P.N + 1);
+      k_update_expansions<M, W, true><<<grid, 128, P.blob_bytes, st>>>(P);
+      return cudaGetLastError();
+    };
+    o.backward_phased = [](const SolverParams& P, cudaStream_t st) -> cudaError_t {
+      const int smem = kBpStages * Lane<M, W>::nexp * kWarp * sizeof(double) + kBpStages * 8;
+      const int grid = (P.T + kWarp / W - 1) / (kWarp / W);
+      cudaError_t e = cudaFuncSetAttribute(k_backward_mat<M, W, kBpStages, false, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      k_backward_mat<M, W, kBpStages, false, true><<<grid, kWarp, smem, st>>>(P);
+      return cudaGetLastError();
+    };
+    o.ls_wide = [](const SolverParams& P, int mode, cudaStream_t st) -> cudaError_t {
+      const int smem = ((P.blob_bytes + 15) / 16) * 16 + kLsWarps * p_stage_doubles<M>(P.pmax, W) * sizeof(double);
+      cudaError_t e = cudaFuncSetAttribute(k_ls_wide<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      k_ls_wide<M, W><<<(P.T + kLsWarps - 1) / kLsWarps, kLsWarps * kWarp, smem, st>>>(P, mode);
+      return cudaGetLastError();
+    };
+    o.ls_deep = [](const SolverParams& P, int mode, int max_instances, cudaStream_t st) -> cudaError_t {
+      const int smem = ((P.blob_bytes + 15) / 16) * 16 + kLsWarps * p_stage_doubles<M>(P.pmax, 1) * sizeof(double);
+      cudaError_t e = cudaFuncSetAttribute(k_ls_deep<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return e;
+      k_ls_deep<M, W><<<(max_instances + kLsWarps - 1) / kLsWarps, kLsWarps * kWarp, smem, st>>>(P, mode, kWarp / W);
+      return cudaGetLastError();
+    };
+  }
   return o;
 }
 
@@ -211,7 +264,7 @@ Ops make_large_ops_32_8() {
   o.expansions = nullptr;
   o.backward_mat = nullptr;
   o.con_values = nullptr;
-  o.solve = [](const SolverParams& P, int mode, int, cudaStream_t st) -> cudaError_t {
+  o.solve = [](const SolverParams& P, int mode, int, int, cudaStream_t st) -> cudaError_t {
     return altro_b200_launch_solve_large_32_8(P, mode, st);
   };
   return o;
@@ -248,6 +301,16 @@ int resident_warps_per_sm(int W) {
 // Tile width: the narrowest tile (most warps, most lane groups for the parallel line search and
 // the knot-parallel backward sweep) whose warps are all resident at once — a second wave would
 // double the makespan of these latency-bound sweeps.
+int g_default_engine = -1;  // -1: not set through the API -> environment, then built-in default
+int default_engine() {
+  if (g_default_engine >= 0) return g_default_engine;
+  if (const char* e = std::getenv("ALTRO_B200_ENGINE")) {
+    if (std::strcmp(e, "fused") == 0) return ALTRO_B200_ENGINE_FUSED;
+    if (std::strcmp(e, "phased") == 0) return ALTRO_B200_ENGINE_PHASED;
+  }
+  return ALTRO_B200_ENGINE_PHASED;
+}
+
 int choose_tile_width(int batch, int sm_count) {
   if (const char* e = std::getenv("ALTRO_B200_TILE")) {
     const int w = std::atoi(e);
@@ -268,6 +331,7 @@ int choose_tile_width(int batch, int sm_count) {
 // ------------------------------------------------------------------------------------------
 struct altro_b200_solver {
   int n, m, N, B, T, Bp, W, G, pmax, device, use_al;
+  int engine = ALTRO_B200_ENGINE_FUSED;
   Ops ops;
   SolverParams P;
   char* d_blob = nullptr;
@@ -289,6 +353,8 @@ struct altro_b200_solver {
   } sec[2];
   int* d_list = nullptr;
   int* h_count = nullptr;  // pinned
+  cudaStream_t st2 = nullptr;            // phased engine, overlapped mode: outer-step kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   int alloc(void** p, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes);
@@ -306,14 +372,30 @@ struct altro_b200_solver {
     dev_bytes += bytes;
     return 0;
   }
+  int ensure_phased() {  // scratch of the phased engine: expansions, deep line-search candidates, list
+    const size_t knots = static_cast<size_t>(T) * (N + 1) * W * sizeof(double);
+    int rc;
+    if (!P.EXP) {
+      if ((rc = alloc(reinterpret_cast<void**>(&P.EXP), knots * exp_fields(n, m)))) return rc;
+      cudaMemset(P.EXP, 0, knots * exp_fields(n, m));
+    }
+    if (!P.CAND) {
+      const size_t bytes = static_cast<size_t>(Bp) * (N + 1) * (n + m) * kWarp * sizeof(double);
+      if ((rc = alloc(reinterpret_cast<void**>(&P.CAND), bytes))) return rc;
+    }
+    if (!P.list && (rc = alloc(reinterpret_cast<void**>(&P.list), static_cast<size_t>(Bp) * sizeof(int)))) return rc;
+    return 0;
+  }
   int ensure_stepwise() {  // EXP / CTG / COSTS are only needed by the step-wise API
     const size_t knots = static_cast<size_t>(T) * (N + 1) * W * sizeof(double);
+    int rc;
     if (!P.EXP) {
-      int rc;
       if ((rc = alloc(reinterpret_cast<void**>(&P.EXP), knots * exp_fields(n, m)))) return rc;
+      cudaMemset(P.EXP, 0, knots * exp_fields(n, m));
+    }
+    if (!P.CTG) {
       if ((rc = alloc(reinterpret_cast<void**>(&P.CTG), knots * (n * n + n)))) return rc;
       if ((rc = alloc(reinterpret_cast<void**>(&P.COSTS), knots))) return rc;
-      cudaMemset(P.EXP, 0, knots * exp_fields(n, m));
       cudaMemset(P.CTG, 0, knots * (n * n + n));
       cudaMemset(P.COSTS, 0, knots);
     }
@@ -345,6 +427,7 @@ DevOptions to_dev(const altro_b200_options& o) {
   d.check_forwardpass_bounds = o.check_forwardpass_bounds;
   d.line_search_max_iterations = o.line_search_max_iterations;
   d.reset_duals = o.reset_duals;
+  d.skip_repeated_iterations = o.skip_repeated_iterations;
   d.cost_tolerance = o.cost_tolerance;
   d.gradient_tolerance = o.gradient_tolerance;
   d.bp_reg_increase_factor = o.bp_reg_increase_factor;
@@ -588,7 +671,12 @@ int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_con
     return fail(ALTRO_B200_ERR_UNSUPPORTED, "the large-state path (n=32) supports unconstrained problems only");
   if (probe.large && static_cast<int>(p->params.size()) != p->n * (p->n + p->m))
     return fail(ALTRO_B200_ERR_ARG, "linear model needs params = [A (n*n), B (n*m)]");
+  s->engine = probe.large ? ALTRO_B200_ENGINE_FUSED : default_engine();
   s->W = probe.large ? 1 : choose_tile_width(batch, sm_count);
+  if (s->engine == ALTRO_B200_ENGINE_PHASED) {
+    if (std::getenv("ALTRO_B200_TILE") && s->W != kPhasedTile) s->engine = ALTRO_B200_ENGINE_FUSED;
+    else s->W = kPhasedTile;
+  }
   s->G = probe.large ? 1 : kWarp / s->W;
   s->T = (batch + s->W - 1) / s->W;
   s->Bp = s->T * s->W;
@@ -618,9 +706,9 @@ int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_con
   if ((rc = s->alloc(reinterpret_cast<void**>(&P.X0), static_cast<size_t>(s->Bp) * p->n * sizeof(double)))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&P.sc), static_cast<size_t>(S_NUM) * s->Bp * sizeof(double)))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&P.is), static_cast<size_t>(I_NUM) * s->Bp * sizeof(int)))) return rc;
-  if ((rc = s->alloc(reinterpret_cast<void**>(&P.counters), 4 * sizeof(int)))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&P.counters), 8 * sizeof(int)))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&s->d_list), static_cast<size_t>(s->Bp) * sizeof(int)))) return rc;
-  CU(cudaMemset(P.counters, 0, 4 * sizeof(int)));
+  CU(cudaMemset(P.counters, 0, 8 * sizeof(int)));
   CU(cudaHostAlloc(reinterpret_cast<void**>(&s->h_count), 4 * sizeof(int), cudaHostAllocDefault));
   s->model = p->model;
   s->sm_count = sm_count;
@@ -654,6 +742,9 @@ void altro_b200_solver_destroy(altro_b200_solver* s) {
       if (w.P.Z[zb]) cudaFree(w.P.Z[zb]);
   if (s->d_io) cudaFree(s->d_io);
   if (s->h_count) cudaFreeHost(s->h_count);
+  if (s->st2) cudaStreamDestroy(s->st2);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->ev_join) cudaEventDestroy(s->ev_join);
   delete s;
 }
 
@@ -742,7 +833,7 @@ static int ensure_secondary(altro_b200_solver* s, int which) {
   if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.X0), static_cast<size_t>(cap) * s->n * sizeof(double)))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.sc), static_cast<size_t>(S_NUM) * cap * sizeof(double)))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.is), static_cast<size_t>(I_NUM) * cap * sizeof(int)))) return rc;
-  if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.counters), 4 * sizeof(int)))) return rc;
+  if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.counters), 8 * sizeof(int)))) return rc;
   w.allocated = true;
   return 0;
 }
@@ -803,7 +894,7 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
   for (int launch = 0; launch < 100000; ++launch) {
     cur->opt = s->P.opt;
     CU(cudaMemsetAsync(cur->counters, 0, 4 * sizeof(int), st));
-    cudaError_t e = cur_ops.solve(*cur, mode, budget, st);
+    cudaError_t e = cur_ops.solve(*cur, mode, budget, 3, st);
     s->launches += 1;
     if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("k_solve launch: ") + cudaGetErrorString(e));
     CU(cudaMemcpyAsync(s->h_count, cur->counters, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -842,8 +933,129 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
   if (cur_sec >= 0 && (rc = scatter_back(*cur))) return rc;
   return 0;
 }
-int altro_b200_solve_al(altro_b200_solver* s, void* stream) { return solve_impl(s, 1, S(stream)); }
-int altro_b200_solve_ilqr(altro_b200_solver* s, void* stream) { return solve_impl(s, 0, S(stream)); }
+// The same solve on the phased engine (phased.cuh): every slot is k_solve(outer/start parts) ->
+// expansions -> TMA-streamed backward pass -> wide line search -> deep line search, all queued
+// on the stream without host round trips; every `poll` slots the host reads the unfinished
+// count and, when enough instances are done, re-packs the rest densely.
+static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
+  DeviceGuard guard(s->device);
+  const int poll = std::max(1, env_int("ALTRO_B200_POLL", 4));
+  const int repack_pct = env_int("ALTRO_B200_REPACK_PCT", 70);  // 0 disables re-packing
+  int rc;
+  if ((rc = s->ensure_phased())) return rc;
+  if ((rc = fill_int(s, I_PHASE, mode == 1 ? kPhAlInit : kPhSolveStart, st))) return rc;
+  if ((rc = fill_int(s, I_LSFAIL, 0, st))) return rc;
+  k_iota<<<(s->Bp + 255) / 256, 256, 0, st>>>(s->P.is + static_cast<size_t>(I_ORIG) * s->Bp, s->Bp);
+  if ((rc = check_launch(s, 1))) return rc;
+  SolverParams* cur = &s->P;
+  Ops cur_ops = s->ops;
+  int cur_sec = -1;
+  auto scatter_back = [&](SolverParams& from) -> int {
+    dim3 grid((from.B + 127) / 128, s->N + 2);
+    k_move_instances<<<grid, 128, 0, st>>>(from, s->P, nullptr, from.B, 1);
+    return check_launch(s, 1);
+  };
+#define PH(call, what)                                                                     \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    s->launches += 1;                                                                      \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(ALTRO_B200_ERR_CUDA, std::string(what " launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+  const bool overlap = env_int("ALTRO_B200_OVERLAP", 1) != 0;
+  if (overlap && !s->st2) {
+    CU(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+  }
+  const int lsmode = mode | (overlap ? 2 : 0);
+  for (long slot = 0; slot < 10000000; ++slot) {
+    cur->opt = s->P.opt;
+    CU(cudaMemsetAsync(cur->counters, 0, 8 * sizeof(int), st));
+    const bool polling = (slot % poll) == 0;
+    if (overlap) {
+      // outer steps / solve starts / final costs on st2, concurrent with the inner iteration of
+      // the instances that were in kPhInner at the slot boundary
+      k_promote<<<(cur->B + 255) / 256, 256, 0, st>>>(*cur);
+      if ((rc = check_launch(s, 1))) return rc;
+      CU(cudaEventRecord(s->ev_fork, st));
+      CU(cudaStreamWaitEvent(s->st2, s->ev_fork, 0));
+      PH(cur_ops.solve(*cur, mode, 1, 1 | 4, s->st2), "k_solve");
+      if (polling) CU(cudaMemcpyAsync(s->h_count, cur->counters, sizeof(int), cudaMemcpyDeviceToHost, s->st2));
+      CU(cudaEventRecord(s->ev_join, s->st2));
+    } else {
+      PH(cur_ops.solve(*cur, mode, 1, 1, st), "k_solve");
+      if (polling) CU(cudaMemcpyAsync(s->h_count, cur->counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    PH(cur_ops.expansions_phased(*cur, st), "k_update_expansions");
+    PH(cur_ops.backward_phased(*cur, st), "k_backward_mat");
+    PH(cur_ops.ls_wide(*cur, lsmode, st), "k_ls_wide");
+    PH(cur_ops.ls_deep(*cur, lsmode, cur->B, st), "k_ls_deep");
+    if (overlap) CU(cudaStreamWaitEvent(st, s->ev_join, 0));
+    if (!polling) continue;
+    CU(cudaStreamSynchronize(st));
+    const int unfinished = s->h_count[0];
+    if (unfinished == 0) break;
+    if (repack_pct > 0 && static_cast<long>(unfinished) * 100 <= static_cast<long>(cur->B) * repack_pct) {
+      const int nxt = (cur_sec == 0) ? 1 : 0;
+      if ((rc = ensure_secondary(s, nxt))) return rc;
+      altro_b200_solver::Secondary& w = s->sec[nxt];
+      CU(cudaMemsetAsync(cur->counters, 0, 8 * sizeof(int), st));
+      k_list_unfinished<<<(cur->B + 255) / 256, 256, 0, st>>>(*cur, s->d_list, unfinished);
+      if ((rc = check_launch(s, 1))) return rc;
+      SolverParams& Q = w.P;
+      Q.B = unfinished;
+      Q.W = kPhasedTile;
+      if ((rc = ensure_secondary_buffers(s, nxt, 1 + kWarp / Q.W, unfinished))) return rc;
+      Q.T = (unfinished + Q.W - 1) / Q.W;
+      Q.Bp = Q.T * Q.W;
+      Q.N = s->N; Q.n = s->n; Q.m = s->m; Q.pmax = s->pmax; Q.use_al = s->use_al;
+      Q.blob = s->P.blob; Q.blob_bytes = s->P.blob_bytes;
+      Q.EXP = s->P.EXP; Q.CAND = s->P.CAND; Q.list = s->P.list;  // per-slot scratch, shared
+      lookup_ops(s->n, s->m, s->model, Q.W, &w.ops);
+      dim3 grid((unfinished + 127) / 128, s->N + 2);
+      k_move_instances<<<grid, 128, 0, st>>>(*cur, Q, s->d_list, unfinished, 0);
+      if ((rc = check_launch(s, 1))) return rc;
+      if (cur_sec >= 0 && (rc = scatter_back(*cur))) return rc;
+      cur = &Q;
+      cur_ops = w.ops;
+      cur_sec = nxt;
+    }
+  }
+#undef PH
+  if (cur_sec >= 0 && (rc = scatter_back(*cur))) return rc;
+  return 0;
+}
+
+static int solve_dispatch(altro_b200_solver* s, int mode, cudaStream_t st) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
+  if (s->engine == ALTRO_B200_ENGINE_PHASED && s->ops.ls_wide) return solve_phased_impl(s, mode, st);
+  return solve_impl(s, mode, st);
+}
+int altro_b200_solve_al(altro_b200_solver* s, void* stream) { return solve_dispatch(s, 1, S(stream)); }
+int altro_b200_solve_ilqr(altro_b200_solver* s, void* stream) { return solve_dispatch(s, 0, S(stream)); }
+/* latency probe of the per-knot device functions (tools/gpu_microbench.py); cycles[16] */
+int altro_b200_microbench(altro_b200_solver* s, long long* cycles, int reps) {
+  if (!s || !cycles || !s->ops.microbench) return fail(ALTRO_B200_ERR_UNSUPPORTED, "microbench: unsupported solver");
+  DeviceGuard guard(s->device);
+  double* sink = nullptr;
+  long long* out = nullptr;
+  CU(cudaMalloc(&sink, 32 * sizeof(double)));
+  CU(cudaMalloc(&out, 16 * sizeof(long long)));
+  CU(cudaMemset(out, 0, 16 * sizeof(long long)));
+  cudaError_t e = s->ops.microbench(s->P, sink, out, reps, 0);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(cycles, out, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(sink);
+  cudaFree(out);
+  if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("microbench: ") + cudaGetErrorString(e));
+  return 0;
+}
+void altro_b200_set_default_engine(int engine) {
+  g_default_engine = (engine == ALTRO_B200_ENGINE_FUSED || engine == ALTRO_B200_ENGINE_PHASED) ? engine : -1;
+}
+int altro_b200_solver_engine(const altro_b200_solver* s) { return s ? s->engine : -1; }
 
 int altro_b200_solve_al_host(altro_b200_solver* s, const double* x0, const double* U0, const double* u_nominal,
                              double* X, double* U, double* cost, double* viol, int32_t* status,

@@ -64,6 +64,10 @@ struct ConBlock {
 struct ConSet {
   int nblocks;
   int p_total;
+  int _pad[2];
+  // packed copy of the scalar fields of blk[i], one 16-byte load per block:
+  // x = kind | equality << 8 | p << 16, y = row0, z = nl, w = xi | yi << 8
+  int4 hdr[kMaxBlocks];
   ConBlock blk[kMaxBlocks];
 };
 
@@ -73,8 +77,8 @@ struct BlobHeader {
   int n, m, N, model;
   int ncost, nconset, pmax, nparams;
   int cost_stride;     // doubles per QuadraticCost: n*n + m*m + n*m + n + m + 1
-  int off_cost_id;     // int[N+1]
-  int off_conset_id;   // int[N+1]
+  int off_cost_id;     // int[N+1]: byte offset (from the blob base) of knot k's QuadraticCost
+  int off_conset_id;   // int[N+1]: byte offset of knot k's ConSet
   int off_h;           // float[N+1]
   int off_t;           // float[N+1]
   int off_params;      // double[nparams]
@@ -84,39 +88,48 @@ struct BlobHeader {
   int _pad;
 };
 
-// Device view of a blob.
+// Device view of a blob.  The table offsets are read once; every per-knot lookup is then a single
+// shared-memory load (the tables hold byte offsets, not ids).
 struct Desc {
   const char* base;
-  __device__ __forceinline__ explicit Desc(const char* b) : base(b) {}
+  const int* cost_off;
+  const int* conset_off;
+  const float* hs;
+  const double* prm;
+  __device__ __forceinline__ explicit Desc(const char* b) : base(b) {
+    if (b) {
+      const BlobHeader& h = *reinterpret_cast<const BlobHeader*>(b);
+      cost_off = reinterpret_cast<const int*>(b + h.off_cost_id);
+      conset_off = reinterpret_cast<const int*>(b + h.off_conset_id);
+      hs = reinterpret_cast<const float*>(b + h.off_h);
+      prm = reinterpret_cast<const double*>(b + h.off_params);
+    } else {
+      cost_off = conset_off = nullptr;
+      hs = nullptr;
+      prm = nullptr;
+    }
+  }
   __device__ __forceinline__ const BlobHeader& hdr() const {
     return *reinterpret_cast<const BlobHeader*>(base);
   }
   __device__ __forceinline__ const double* cost(int k) const {
-    const BlobHeader& h = hdr();
-    const int id = reinterpret_cast<const int*>(base + h.off_cost_id)[k];
-    return reinterpret_cast<const double*>(base + h.off_cost) + id * h.cost_stride;
+    return reinterpret_cast<const double*>(base + cost_off[k]);
   }
   __device__ __forceinline__ const ConSet& conset(int k) const {
-    const BlobHeader& h = hdr();
-    const int id = reinterpret_cast<const int*>(base + h.off_conset_id)[k];
-    return reinterpret_cast<const ConSet*>(base + h.off_conset)[id];
+    return *reinterpret_cast<const ConSet*>(base + conset_off[k]);
   }
-  __device__ __forceinline__ float h(int k) const {
-    return reinterpret_cast<const float*>(base + hdr().off_h)[k];
-  }
+  __device__ __forceinline__ float h(int k) const { return hs[k]; }
   __device__ __forceinline__ float t(int k) const {
     return reinterpret_cast<const float*>(base + hdr().off_t)[k];
   }
-  __device__ __forceinline__ const double* params() const {
-    return reinterpret_cast<const double*>(base + hdr().off_params);
-  }
+  __device__ __forceinline__ const double* params() const { return prm; }
 };
 
 // altro/common/solver_options.hpp:19-65 (numeric fields)
 struct DevOptions {
   int max_iterations_total, max_iterations_outer, max_iterations_inner;
   int bp_reg_fail_threshold, check_forwardpass_bounds, line_search_max_iterations, reset_duals;
-  int _pad;
+  int skip_repeated_iterations;  // extension, default 0 (see finish_inner in kernels.cuh)
   double cost_tolerance, gradient_tolerance;
   double bp_reg_increase_factor, bp_reg_initial, bp_reg_max, bp_reg_min;
   double state_max, control_max;
@@ -139,6 +152,8 @@ enum ScalarField : int {
   S_CSRC_ALPHA,    // Q8: < 0 -> stored constraint values come from Z; else alpha of the last
                    //        evaluated (rejected) candidate
   S_J0,            // costs_.sum() of the current Z_ (carried between launches of k_solve)
+  S_GS_BWD,        // sum_k max_i |d_i|/(|u_i|+1) of the last backward pass (phased engine hand-off)
+  S_REG_IN, S_DREG_IN,  // regularisation at the entry of the current inner iteration (phased engine hand-off)
   S_NUM
 };
 enum IntField : int {
@@ -162,6 +177,12 @@ enum SolvePhase : int {
   kPhDone = 4,        // terminated; final Cost() not reported yet
   kPhReported = 5,    // everything written
   kPhMoved = 6,       // continued in another workspace
+  // phased engine, overlapped mode: the outer-step kernel of a slot runs concurrently with the
+  // inner-iteration kernels of the other instances; a transition made during a slot becomes
+  // visible to the other kernel group only at the next slot boundary (k_promote)
+  kPhInnerPending = -1,
+  kPhOuterPending = -2,
+  kPhDonePending = -3,
 };
 
 struct SolverParams {
@@ -174,12 +195,15 @@ struct SolverParams {
   double* KD;     // [T][N][m*n+m][W]       K (col-major m x n) then d
   double* LAM;    // [T][N+1][pmax][W]      duals (nullptr when pmax == 0)
   double* X0;     // [T][n][W]              initial states
-  double* EXP;    // [T][N+1][fexp][W]      materialised expansions (step-wise API only)
+  double* EXP;    // [T][N+1][fexp][W]      materialised expansions (step-wise API, phased engine)
   double* CTG;    // [T][N+1][n*n+n][W]     cost-to-go P, p (step-wise API only)
   double* COSTS;  // [T][N+1][W]            costs_ vector (step-wise API only)
   double* sc;     // [S_NUM][Bp]
   int* is;        // [I_NUM][Bp]
-  int* counters;  // [0] = instances not yet reported after the last k_solve launch
+  int* counters;  // [0] = instances not yet reported after the last k_solve launch; [1],[2] re-pack
+                  // cursors; [3] = entries of `list` (phased engine); 8 ints
+  int* list;      // [Bp] phased engine: instances whose line search continues in k_ls_deep
+  double* CAND;   // [Bp][N+1][n+m][32]  phased engine: candidate trajectories of k_ls_deep (scratch)
   DevOptions opt;
 };
 

@@ -388,125 +388,228 @@ __device__ __forceinline__ double con_row_fast(const ConBlock& b, int i, const d
   }
 }
 
+// Pi_{K*} for the negative orthant: min(0, x) (constraint.hpp:98-104).  Same value as
+// fmin(0.0, x) for every x including NaN, in 3 instructions instead of 8.
+__device__ __forceinline__ double neg_part(double x) { return x < 0.0 ? x : 0.0; }
+
+// Rows of one constraint block, four at a time.  The per-row control flow of an interpreter
+// (load kind -> branch -> load operands -> compute) serialises on shared-memory latency; here
+// the kind is resolved once per block and a chunk's operand loads and constraint values are
+// independent, so they overlap.  f(c, ic, ok) receives the values c[q] of rows ic[q] = r0 + q;
+// rows past the block's end have ok[q] = false and repeat the last row (to be masked by f).
+constexpr int kChunk = 4;
+
+// scalar fields of a constraint block, unpacked from ConSet::hdr (one 16-byte load)
+struct BlockHdr {
+  int kind, p, row0, nl, xi, yi;
+  bool eq;
+  __device__ __forceinline__ explicit BlockHdr(const int4& h)
+      : kind(h.x & 0xff), p(h.x >> 16), row0(h.y), nl(h.z), xi(h.w & 0xff), yi(h.w >> 8), eq(((h.x >> 8) & 1) != 0) {}
+};
+
+// penalty and the reciprocal used by `/ (2 rho)` (constraint_values.hpp:118), computed once per sweep
+struct AlPen {
+  double rho, two_rho, r_two_rho;
+  __device__ __forceinline__ explicit AlPen(double r) : rho(r), two_rho(2 * r), r_two_rho(1.0 / (2 * r)) {}
+};
+
+template <int n, int m, class F>
+__device__ __forceinline__ void for_row_chunks(const BlockHdr& hd, const ConBlock& b, const double* x,
+                                               const double* u, F&& f) {
+  const int p = hd.p;
+  if (hd.kind == kCircle) {
+    const double px = pick<n>(x, hd.xi), py = pick<n>(x, hd.yi);
+    for (int r0 = 0; r0 < p; r0 += kChunk) {
+      double c[kChunk];
+      int ic[kChunk];
+      bool ok[kChunk];
+      ALTRO_UNROLL
+      for (int q = 0; q < kChunk; ++q) {
+        ok[q] = r0 + q < p;
+        ic[q] = ok[q] ? r0 + q : p - 1;
+        const double dx = px - b.a[ic[q]], dy = py - b.b[ic[q]];
+        c[q] = -(dx * dx + dy * dy - b.c[ic[q]] * b.c[ic[q]]);  // obstacle_constraints.hpp:107-110
+      }
+      f(c, ic, ok);
+    }
+  } else if (hd.kind == kControlBound) {
+    const int nl = hd.nl;
+    for (int r0 = 0; r0 < p; r0 += kChunk) {
+      double c[kChunk];
+      int ic[kChunk];
+      bool ok[kChunk];
+      ALTRO_UNROLL
+      for (int q = 0; q < kChunk; ++q) {
+        ok[q] = r0 + q < p;
+        ic[q] = ok[q] ? r0 + q : p - 1;
+        const double uj = pick<m>(u, b.idx[ic[q]]);
+        c[q] = (ic[q] < nl) ? (b.a[ic[q]] - uj) : (uj - b.a[ic[q]]);  // basic_constraints.hpp:110-118
+      }
+      f(c, ic, ok);
+    }
+  } else {  // kGoal: c = x - xf (basic_constraints.hpp:31)
+    for (int r0 = 0; r0 < p; r0 += kChunk) {
+      double c[kChunk];
+      int ic[kChunk];
+      bool ok[kChunk];
+      ALTRO_UNROLL
+      for (int q = 0; q < kChunk; ++q) {
+        ok[q] = r0 + q < p;
+        ic[q] = ok[q] ? r0 + q : p - 1;
+        c[q] = pick<n>(x, ic[q]) - b.a[ic[q]];
+      }
+      f(c, ic, ok);
+    }
+  }
+}
+
 // Adds the AL value of every constraint of a knot to J, one constraint at a time
 // (al_cost.hpp:266-272); also returns the max violation |c - Pi_K(c)|_inf
 // (constraint_values.hpp:216-221).
 template <int n, int m, int LS>
 __device__ __forceinline__ double al_value(const ConSet& cs, const double* x, const double* u,
-                                           const double* lam, double rho, double J,
+                                           const double* lam, const AlPen& pen, double J,
                                            double* viol) {
   double v = 0.0;
-  const double two_rho = 2 * rho;
-  const double r_two_rho = (cs.nblocks > 0) ? 1.0 / two_rho : 0.0;
-  for (int bi = 0; bi < cs.nblocks; ++bi) {
-    const ConBlock& b = cs.blk[bi];
-    double sa = 0.0, sb = 0.0;
-    double px = 0.0, py = 0.0;
-    if (b.kind == kCircle) {  // loop-invariant position of the circle rows
-      px = pick<n>(x, b.xi);
-      py = pick<n>(x, b.yi);
+  const double rho = pen.rho;
+  const int nblocks = cs.nblocks;
+  int4 hraw[kMaxBlocks];
+  ALTRO_UNROLL
+  for (int bi = 0; bi < kMaxBlocks; ++bi) hraw[bi] = cs.hdr[bi];  // all block headers at once
+  ALTRO_UNROLL
+  for (int bi = 0; bi < kMaxBlocks; ++bi) {
+    if (bi < nblocks) {
+      const BlockHdr hd(hraw[bi]);
+      const ConBlock& b = cs.blk[bi];
+      const bool eq = hd.eq;
+      const double* lb = lam + hd.row0 * LS;
+      double sa = 0.0, sb = 0.0;
+      for_row_chunks<n, m>(hd, b, x, u, [&](const double* c, const int* ic, const bool* ok) {
+        double l[kChunk], lp[kChunk];
+        ALTRO_UNROLL
+        for (int q = 0; q < kChunk; ++q) {
+          l[q] = lb[ic[q] * LS];
+          const double arg = l[q] - rho * c[q];
+          lp[q] = eq ? arg : neg_part(arg);
+        }
+        ALTRO_UNROLL
+        for (int q = 0; q < kChunk; ++q) {
+          if (ok[q]) {
+            sa += lp[q] * lp[q];
+            sb += l[q] * l[q];
+            v = fmax(v, eq ? fabs(c[q]) : fabs(c[q] - neg_part(c[q])));
+          }
+        }
+      });
+      double Jb = sa - sb;
+      Jb = div_by(Jb, pen.two_rho, pen.r_two_rho);
+      J += Jb;
     }
-    for (int i = 0; i < b.p; ++i) {
-      double c;
-      if (b.kind == kCircle) {
-        const double dx = px - b.a[i], dy = py - b.b[i];
-        c = -(dx * dx + dy * dy - b.c[i] * b.c[i]);
-      } else {
-        c = con_row_fast<n, m>(b, i, x, u);
-      }
-      const double l = lam[(b.row0 + i) * LS];
-      const double arg = l - rho * c;
-      const double lp = b.equality ? arg : fmin(0.0, arg);
-      sa += lp * lp;
-      sb += l * l;
-      v = fmax(v, b.equality ? fabs(c) : fabs(c - fmin(0.0, c)));
-    }
-    double Jb = sa - sb;
-    Jb = div_by(Jb, two_rho, r_two_rho);
-    J += Jb;
   }
   if (viol) *viol = v;
   return J;
 }
 
 // Adds the AL gradient and Gauss-Newton Hessian of every constraint of the knot to the cost
-// expansion (which already holds the QuadraticCost terms).
+// expansion (which already holds the QuadraticCost terms).  Per constraint the reference forms
+// dx = -(dPi dc)^T Pi(lam - rho c) and dxdx = rho (dPi dc)^T (dPi dc) as matrix products (sums
+// over the rows in order) and ALCost adds them to the running expansion
+// (constraint_values.hpp:131-177, al_cost.hpp:280-308); here the products are accumulated
+// row by row in the same order on the few entries the constraint's Jacobian touches.
 template <int n, int m, int LS>
 __device__ __forceinline__ void al_expansion(const ConSet& cs, const double* x, const double* u,
                                              const double* lam, double rho, double* lxx,
                                              double* lxu, double* luu, double* lx, double* lu) {
   (void)lxu;  // none of the device-capable constraints couples x and u
-  for (int bi = 0; bi < cs.nblocks; ++bi) {
+  const int nblocks = cs.nblocks;
+  int4 hraw[kMaxBlocks];
+  ALTRO_UNROLL
+  for (int bi = 0; bi < kMaxBlocks; ++bi) hraw[bi] = cs.hdr[bi];
+  ALTRO_UNROLL
+  for (int bi = 0; bi < kMaxBlocks; ++bi) {
+    if (bi >= nblocks) continue;
+    const BlockHdr hd(hraw[bi]);
     const ConBlock& b = cs.blk[bi];
-    if (b.kind == kGoal) {
+    const double* lb = lam + hd.row0 * LS;
+    if (hd.kind == kGoal) {
       // J = [I | 0], identity dual cone: dx_i = -(lam_i - rho c_i), dxdx_ii = rho
       ALTRO_UNROLL
       for (int i = 0; i < n; ++i) {
-        if (i < b.p) {
+        if (i < hd.p) {
           const double c = x[i] - b.a[i];
-          const double lp = lam[(b.row0 + i) * LS] - rho * c;
+          const double lp = lb[i * LS] - rho * c;
           lx[i] += (-1.0) * lp;
           lxx[i + i * n] += (rho * 1.0) * 1.0;
         }
       }
-    } else if (b.kind == kControlBound) {
+    } else if (hd.kind == kControlBound) {
       // rows [0,nl): c = lb_j - u_j, J = -e_j ; rows [nl,nl+nu): c = u_j - ub_j, J = +e_j.
-      // Per control j the block contributes lower-row term first, then upper-row term.
+      // Per control j the block contributes its lower-row term first, then its upper-row term.
       double gdu[m], gduu[m];
-      bool hit[m];
       ALTRO_UNROLL
-      for (int j = 0; j < m; ++j) { gdu[j] = 0.0; gduu[j] = 0.0; hit[j] = false; }
-      for (int i = 0; i < b.p; ++i) {
-        const int j = b.idx[i];
-        const double uj = pick<m>(u, j);
-        const bool lower = i < b.nl;
-        const double c = lower ? (b.a[i] - uj) : (uj - b.a[i]);
-        const double arg = lam[(b.row0 + i) * LS] - rho * c;
-        const double lp = fmin(0.0, arg);
-        const double act = arg > 0 ? 0.0 : 1.0;      // constraint.hpp:112 (Q12)
-        const double jp = act * (lower ? -1.0 : 1.0);  // proj_jac * jac entry
-        const double g = (-jp) * lp;
-        const double hh = (rho * jp) * jp;
+      for (int j = 0; j < m; ++j) { gdu[j] = 0.0; gduu[j] = 0.0; }
+      const int nl = hd.nl;
+      for_row_chunks<n, m>(hd, b, x, u, [&](const double* c, const int* ic, const bool* ok) {
+        double g[kChunk], hh[kChunk];
+        int jj[kChunk];
         ALTRO_UNROLL
-        for (int jj = 0; jj < m; ++jj) {
-          if (jj == j) {
-            gdu[jj] = hit[jj] ? gdu[jj] + g : g;
-            gduu[jj] = hit[jj] ? gduu[jj] + hh : hh;
-            hit[jj] = true;
+        for (int q = 0; q < kChunk; ++q) {
+          jj[q] = ok[q] ? b.idx[ic[q]] : -1;
+          const double arg = lb[ic[q] * LS] - rho * c[q];
+          const double lp = neg_part(arg);
+          const double act = arg > 0 ? 0.0 : 1.0;               // constraint.hpp:112 (Q12)
+          const double jp = act * (ic[q] < nl ? -1.0 : 1.0);    // proj_jac * jac entry
+          g[q] = (-jp) * lp;
+          hh[q] = (rho * jp) * jp;
+        }
+        ALTRO_UNROLL
+        for (int q = 0; q < kChunk; ++q) {
+          ALTRO_UNROLL
+          for (int j = 0; j < m; ++j) {
+            if (jj[q] == j) {
+              gdu[j] += g[q];
+              gduu[j] += hh[q];
+            }
           }
         }
-      }
+      });
       ALTRO_UNROLL
       for (int j = 0; j < m; ++j) {
-        if (hit[j]) {
-          lu[j] += gdu[j];
-          luu[j + j * m] += gduu[j];
-        }
+        lu[j] += gdu[j];
+        luu[j + j * m] += gduu[j];
       }
     } else {
       // circles: J(i, 0) = 2(cx - px), J(i, 1) = 2(cy - py) — columns 0 and 1 as the
       // reference writes them (obstacle_constraints.hpp:117-118).
       static_assert(n >= 2, "circle constraints need two position states");
-      const double px = pick<n>(x, b.xi), py = pick<n>(x, b.yi);
+      const double px = pick<n>(x, hd.xi), py = pick<n>(x, hd.yi);
       double g0 = 0.0, g1 = 0.0, h00 = 0.0, h01 = 0.0, h10 = 0.0, h11 = 0.0;
-      for (int i = 0; i < b.p; ++i) {
-        const double dx = px - b.a[i], dy = py - b.b[i];
-        const double c = -(dx * dx + dy * dy - b.c[i] * b.c[i]);
-        const double arg = lam[(b.row0 + i) * LS] - rho * c;
-        const double lp = fmin(0.0, arg);
-        const double act = arg > 0 ? 0.0 : 1.0;
-        const double j0 = act * (2 * (b.a[i] - px));
-        const double j1 = act * (2 * (b.b[i] - py));
-        const double t0 = (-j0) * lp, t1 = (-j1) * lp;
-        const double r0 = rho * j0, r1 = rho * j1;
-        if (i == 0) {
-          g0 = t0; g1 = t1;
-          h00 = r0 * j0; h01 = r0 * j1; h10 = r1 * j0; h11 = r1 * j1;
-        } else {
-          g0 += t0; g1 += t1;
-          h00 += r0 * j0; h01 += r0 * j1; h10 += r1 * j0; h11 += r1 * j1;
+      for_row_chunks<n, m>(hd, b, x, u, [&](const double* c, const int* ic, const bool* ok) {
+        double j0[kChunk], j1[kChunk], t0[kChunk], t1[kChunk], r0[kChunk], r1[kChunk];
+        ALTRO_UNROLL
+        for (int q = 0; q < kChunk; ++q) {
+          const double arg = lb[ic[q] * LS] - rho * c[q];
+          const double lp = neg_part(arg);
+          const double act = (ok[q] && !(arg > 0)) ? 1.0 : 0.0;
+          j0[q] = act * (2 * (b.a[ic[q]] - px));
+          j1[q] = act * (2 * (b.b[ic[q]] - py));
+          t0[q] = (-j0[q]) * lp;
+          t1[q] = (-j1[q]) * lp;
+          r0[q] = rho * j0[q];
+          r1[q] = rho * j1[q];
         }
-      }
+        ALTRO_UNROLL
+        for (int q = 0; q < kChunk; ++q) {
+          if (ok[q]) {
+            g0 += t0[q];
+            g1 += t1[q];
+            h00 += r0[q] * j0[q];
+            h01 += r0[q] * j1[q];
+            h10 += r1[q] * j0[q];
+            h11 += r1[q] * j1[q];
+          }
+        }
+      });
       lx[0] += g0;
       lx[1] += g1;
       lxx[0 + 0 * n] += h00;
@@ -520,10 +623,10 @@ __device__ __forceinline__ void al_expansion(const ConSet& cs, const double* x, 
 // ALCost::Evaluate (al_cost.hpp:264-274) for knot k.
 template <int n, int m, int LS>
 __device__ __forceinline__ double knot_cost(const Desc& D, int k, const double* x,
-                                            const double* u, const double* lam, double rho,
+                                            const double* u, const double* lam, const AlPen& pen,
                                             double* viol) {
   const double J = quad_eval<n, m>(D.cost(k), x, u);
-  return al_value<n, m, LS>(D.conset(k), x, u, lam, rho, J, viol);
+  return al_value<n, m, LS>(D.conset(k), x, u, lam, pen, J, viol);
 }
 
 // Riccati step of the backward pass (knot_point_function_type.hpp:149-230) ----------------

@@ -124,6 +124,7 @@ __device__ __forceinline__ bool sweep_forward(const Lane<M, W>& L, double* stg, 
   const double* mp = D.params();
   const int off_lam = nz + (kClosed ? nkd : 0);
   const int R = off_lam + pmax;
+  const AlPen pen(penalty);
   auto issue = [&](int k) {
     double* s = stg + (k & 1) * R * W + L.i;
     if (L.a == 0) {
@@ -190,7 +191,7 @@ __device__ __forceinline__ bool sweep_forward(const Lane<M, W>& L, double* stg, 
         for (int q = 0; q < m; ++q) zn[(n + q) * W] = u[q];
       }
       double v;
-      Jsum += knot_cost<n, m, W>(D, k, x, u, s + off_lam * W, penalty, &v);
+      Jsum += knot_cost<n, m, W>(D, k, x, u, s + off_lam * W, pen, &v);
       vmax = fmax(vmax, v);
       if (k < N) {
         if (kClosed) gs += g;
@@ -229,6 +230,7 @@ __device__ __forceinline__ double sweep_cost(const Lane<M, W>& L, double* stg, b
   constexpr int n = M::n, m = M::m, nz = n + m;
   const int N = L.P.N, pmax = L.P.pmax;
   const int R = nz + pmax;
+  const AlPen pen(penalty);
   auto issue = [&](int k) {
     double* s = stg + (k & 1) * R * W + L.i;
     if (L.a == 0) {
@@ -257,7 +259,7 @@ __device__ __forceinline__ double sweep_cost(const Lane<M, W>& L, double* stg, b
       ALTRO_UNROLL
       for (int q = 0; q < m; ++q) u[q] = s[(n + q) * W];
       double v;
-      const double c = knot_cost<n, m, W>(L.D, k, x, u, s + nz * W, penalty, &v);
+      const double c = knot_cost<n, m, W>(L.D, k, x, u, s + nz * W, pen, &v);
       if (kStoreCosts) *L.costs(k) = c;
       J += c;
       vmax = fmax(vmax, v);
@@ -466,14 +468,26 @@ __device__ __forceinline__ double sweep_dual(const Lane<M, W>& L, bool active, i
     for (int q = 0; q < m; ++q) u[q] = zc[(n + q) * W];
     for (int bi = 0; bi < cs.nblocks; ++bi) {
       const ConBlock& b = cs.blk[bi];
-      for (int r = 0; r < b.p; ++r) {
-        const double c = con_row_fast<n, m>(b, r, x, u);
+      const BlockHdr hd(cs.hdr[bi]);
+      const bool eq = hd.eq;
+      double* lb = lam + hd.row0 * W;
+      for_row_chunks<n, m>(hd, b, x, u, [&](const double* c, const int* ic, const bool* ok) {
+        double l[kChunk];
         if (update) {
-          const double arg = lam[(b.row0 + r) * W] - penalty * c;
-          lam[(b.row0 + r) * W] = b.equality ? arg : fmin(0.0, arg);
+          ALTRO_UNROLL
+          for (int q = 0; q < kChunk; ++q) l[q] = lb[ic[q] * W];
         }
-        vmax = fmax(vmax, b.equality ? fabs(c) : fabs(c - fmin(0.0, c)));
-      }
+        ALTRO_UNROLL
+        for (int q = 0; q < kChunk; ++q) {
+          if (ok[q]) {
+            if (update) {
+              const double arg = l[q] - penalty * c[q];
+              lb[ic[q] * W] = eq ? arg : neg_part(arg);
+            }
+            vmax = fmax(vmax, eq ? fabs(c[q]) : fabs(c[q] - neg_part(c[q])));
+          }
+        }
+      });
     }
   }
   return vmax;
@@ -565,6 +579,81 @@ __device__ __forceinline__ LineSearchResult line_search(const Lane<M, W>& L, dou
 }
 
 // ------------------------------------------------------------------------------------------
+// Tail of one inner iteration (ilqr.hpp:300-313 after ForwardPass): bookkeeping of the line
+// search outcome, UpdateConvergenceStatistics (:568-587, Q15) and IsDone (:597-619).  Shared by
+// the fused engine (k_solve) and the phased engine (phased.cuh) so both follow the same rules.
+//
+// Stall skip (option skip_repeated_iterations, off by default): when a line search fails
+// completely, Z_, the duals and the penalty stay as they are, so the next iteration differs
+// from this one only through (reg, dreg) at its entry.  If the failed iteration leaves (reg,
+// dreg) exactly where they were at its own entry, every later iteration of this iLQR solve is
+// a bit-identical repetition (same gains, same failed search, dJ = 0, same grad): the remaining
+// ones are accounted for — counters, status — without being executed.  Results are identical.
+// ------------------------------------------------------------------------------------------
+struct InnerTail {
+  bool success;
+  int new_zsel;        // buffer of the accepted trajectory
+  double J, alpha, z, gsum_ls, gsum_bwd;
+  double reg_in, dreg_in;  // regularisation at the entry of this iteration (before BackwardPass)
+};
+
+__device__ __forceinline__ void finish_inner(const DevOptions& o, int N, int mode, const InnerTail& t,
+                                             int& zsel, double& J0, double& cost_cur, double& cost_prev,
+                                             double initial_cost, double& alpha_stat, double& z_stat,
+                                             double& csrc, double& grad, double& dJ, double& reg,
+                                             double& dreg, int& it_inner, int& it_total, int& st,
+                                             int& phase, int& lsfail, int ph_outer = kPhOuter,
+                                             int ph_done = kPhDone) {
+  lsfail = t.success ? 0 : 1;
+  if (t.success) {
+    zsel = t.new_zsel;  // (*Z_) = (*Zbar_)
+    J0 = t.J;
+    cost_cur = t.J;  // stats.Log("cost"/"alpha"/"z")
+    alpha_stat = t.alpha;
+    z_stat = t.z;
+    csrc = -1.0;  // the stored constraint values are those of the new Z_
+    grad = t.gsum_ls / static_cast<double>(N);
+  } else {
+    increase_reg(o, reg, dreg);
+    grad = t.gsum_bwd / static_cast<double>(N);
+  }
+  // UpdateConvergenceStatistics, ilqr.hpp:568-587 (Q15)
+  dJ = (it_inner == 0) ? (initial_cost - cost_cur) : (cost_prev - cost_cur);
+  it_inner++;
+  it_total++;
+  cost_prev = cost_cur;  // NewIteration() carry-forward (Q6)
+  // IsDone, ilqr.hpp:597-619
+  bool done = true;
+  if (dJ < o.cost_tolerance && grad < o.gradient_tolerance) {
+    st = kSolved;
+  } else if (it_inner >= o.max_iterations_inner) {
+    st = kMaxInnerIterations;
+  } else if (it_total >= o.max_iterations_total) {
+    st = kMaxIterations;
+  } else if (st == kUnsolved) {
+    done = false;
+  }
+  if (!done && o.skip_repeated_iterations && !t.success && reg == t.reg_in && dreg == t.dreg_in) {
+    // iterations it_inner+1, ... repeat this one with dJ = 0 and the same grad
+    dJ = 0.0;
+    if (dJ < o.cost_tolerance && grad < o.gradient_tolerance) {
+      it_inner += 1;
+      it_total += 1;
+      st = kSolved;
+    } else {
+      const int left_inner = o.max_iterations_inner - it_inner;
+      const int left_total = o.max_iterations_total - it_total;
+      const int skip = left_inner < left_total ? left_inner : left_total;
+      it_inner += skip;
+      it_total += skip;
+      st = (it_inner >= o.max_iterations_inner) ? kMaxInnerIterations : kMaxIterations;
+    }
+    done = true;
+  }
+  if (done) phase = (mode == 1) ? ph_outer : ph_done;
+}
+
+// ------------------------------------------------------------------------------------------
 // k_solve: the whole AugmentedLagrangianiLQR::Solve (mode 1) / iLQR::Solve (mode 0) as a
 // resumable per-instance state machine, one warp per tile.  A "slot" lets every live instance
 // of the tile do its pending outer-loop work (dual/penalty update, rollout of the next iLQR
@@ -577,7 +666,7 @@ constexpr int kSolveWarps = ALTRO_SOLVE_WARPS;
 
 template <class M, int W>
 __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB_NARROW : ALTRO_SOLVE_MINB)) k_solve(SolverParams P, int mode,
-                                                                               int budget) {
+                                                                               int budget, int parts) {
   extern __shared__ __align__(128) char smem[];
   copy_blob(P.blob, smem, P.blob_bytes);
   const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -624,6 +713,9 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
     lsfail = L.is(I_LSFAIL);
   }
   const bool was_reported = phase >= kPhReported;
+  // overlapped mode of the phased engine (parts & 4): instances in kPhInner belong to the
+  // inner-iteration kernels running concurrently on another stream — hands off their state
+  const bool foreign = (parts & 4) && phase == kPhInner;
   if (phase == kPhAlInit) {  // AugmentedLagrangianiLQR::Init, al_solver.hpp:287-302 (Q10)
     if (o.reset_duals && has_con && L.a == 0) {
       for (int k = 0; k <= N; ++k) {
@@ -645,7 +737,7 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
     if (!__any_sync(kFull, phase < kPhDone)) break;
     // ------------- AL outer step for instances whose iLQR solve just ended ------------------
     // al_solver.hpp:313-333: UpdateDuals, UpdateConvergenceStatistics, IsDone, UpdatePenalties
-    const bool outer = phase == kPhOuter;
+    const bool outer = phase == kPhOuter && (parts & 1);
     if (__any_sync(kFull, outer)) {
       // Q8: after a fully failed line search the stored constraint values are those of the last
       // evaluated candidate; regenerate it (slot 0) so the dual update sees the same values.
@@ -683,10 +775,11 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
       __syncwarp();
     }
     // ------------- iLQR::Solve() entry: SolveSetup, Rollout, initial Cost -------------------
-    const bool start = phase == kPhSolveStart;
+    const bool start = phase == kPhSolveStart && (parts & 1);
     if (__any_sync(kFull, start)) {
       if (start) {
         it_inner = 0;  // SolveSetup :629-645, ResetInternalVariables :680-690
+        lsfail = 0;
         st = kUnsolved;
         reg = o.bp_reg_initial;
         dreg = 0.0;
@@ -700,14 +793,16 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
         J0 = Jr;
         initial_cost = Jr;
         csrc = -1.0;
-        phase = (o.max_iterations_inner > 0) ? kPhInner : (mode == 1 ? kPhOuter : kPhDone);
+        phase = (o.max_iterations_inner > 0) ? ((parts & 4) ? kPhInnerPending : kPhInner)
+                                             : (mode == 1 ? kPhOuter : kPhDone);
       }
     }
     // ------------- one inner iteration, ilqr.hpp:300-313 ------------------------------------
-    const bool run = phase == kPhInner;
+    const bool run = phase == kPhInner && (parts & 2);
     if (__any_sync(kFull, run)) {
       double gs_bwd = 0.0;
       if (run) csrc = -1.0;  // UpdateExpansions evaluates every constraint at Z_
+      const double reg_in = reg, dreg_in = dreg;
       sweep_backward<M, W, false>(L, stg, run, zsel, penalty, reg, dreg, dV0, dV1, st, gs_bwd);
       reg = __shfl_sync(kFull, reg, L.i);
       dreg = __shfl_sync(kFull, dreg, L.i);
@@ -717,36 +812,18 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
       gs_bwd = __shfl_sync(kFull, gs_bwd, L.i);
       const LineSearchResult ls = line_search<M, W>(L, stg, run, zsel, penalty, J0, dV0, dV1, st, csrc);
       if (run) {
-        lsfail = ls.success ? 0 : 1;
-        if (ls.success) {
-          zsel = Lane<M, W>::cand(zsel, ls.slot);  // (*Z_) = (*Zbar_)
-          J0 = ls.J;
-          cost_cur = ls.J;  // stats.Log("cost"/"alpha"/"z")
-          alpha_stat = ls.alpha;
-          z_stat = ls.z;
-          csrc = -1.0;  // the stored constraint values are those of the new Z_
-          grad = ls.gsum / static_cast<double>(N);
-        } else {
-          increase_reg(o, reg, dreg);
-          grad = gs_bwd / static_cast<double>(N);
-        }
-        // UpdateConvergenceStatistics, ilqr.hpp:568-587 (Q15)
-        dJ = (it_inner == 0) ? (initial_cost - cost_cur) : (cost_prev - cost_cur);
-        it_inner++;
-        it_total++;
-        cost_prev = cost_cur;  // NewIteration() carry-forward (Q6)
-        // IsDone, ilqr.hpp:597-619
-        bool done = true;
-        if (dJ < o.cost_tolerance && grad < o.gradient_tolerance) {
-          st = kSolved;
-        } else if (it_inner >= o.max_iterations_inner) {
-          st = kMaxInnerIterations;
-        } else if (it_total >= o.max_iterations_total) {
-          st = kMaxIterations;
-        } else if (st == kUnsolved) {
-          done = false;
-        }
-        if (done) phase = (mode == 1) ? kPhOuter : kPhDone;
+        InnerTail t;
+        t.success = ls.success;
+        t.new_zsel = Lane<M, W>::cand(zsel, ls.slot);
+        t.J = ls.J;
+        t.alpha = ls.alpha;
+        t.z = ls.z;
+        t.gsum_ls = ls.gsum;
+        t.gsum_bwd = gs_bwd;
+        t.reg_in = reg_in;
+        t.dreg_in = dreg_in;
+        finish_inner(o, N, mode, t, zsel, J0, cost_cur, cost_prev, initial_cost, alpha_stat, z_stat, csrc,
+                     grad, dJ, reg, dreg, it_inner, it_total, st, phase, lsfail);
       }
     }
   }
@@ -756,7 +833,8 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
   const bool fin = phase == kPhDone;
   double Jf = 0.0, vf = 0.0;
   if (__any_sync(kFull, fin)) Jf = sweep_cost<M, W, false>(L, stg, fin && L.a == 0, zsel, penalty, &vf);
-  if (lead && !was_reported) {
+  if (lead && !was_reported && foreign) atomicAdd(&P.counters[0], 1);
+  if (lead && !was_reported && !foreign) {
     if (fin) {
       if (mode == 0) viol = vf;  // == Cost(); GetMaxViolation()
       L.sc(S_COST) = Jf;
@@ -807,6 +885,17 @@ __global__ void k_list_unfinished(SolverParams src, int* __restrict__ list, int 
       list[total - 1 - atomicAdd(&src.counters[2], 1)] = b;
     }
   }
+}
+
+// slot boundary of the phased engine in overlapped mode: pending transitions take effect
+__global__ void k_promote(SolverParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  int& ph = P.is[static_cast<size_t>(I_PHASE) * P.Bp + b];
+  const int v = ph;
+  if (v == kPhInnerPending) ph = kPhInner;
+  else if (v == kPhOuterPending) ph = kPhOuter;
+  else if (v == kPhDonePending) ph = kPhDone;
 }
 
 // dst slot j <- src slot list[j]: current trajectory (into buffer 0), gains, duals, x0, scalars.
@@ -1016,7 +1105,9 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp) k_phase(SolverParams P, in
 // ------------------------------------------------------------------------------------------
 // One thread per (instance, knot): fully parallel over B x (N+1), like the reference's
 // thread-pool tasks (ilqr.hpp:354-365) but with the batch as the wide axis.
-template <class M, int W>
+// kPhased: only instances about to run an inner iteration (kPhInner) are expanded and the
+// per-knot costs_ are not stored (the phased engine carries J0 like k_solve does).
+template <class M, int W, bool kPhased = false>
 __global__ void __launch_bounds__(128) k_update_expansions(SolverParams P) {
   extern __shared__ __align__(128) char s_blob[];
   copy_blob(P.blob, s_blob, P.blob_bytes);
@@ -1025,6 +1116,7 @@ __global__ void __launch_bounds__(128) k_update_expansions(SolverParams P) {
   const int k = blockIdx.y;
   if (b >= P.B) return;
   const Lane<M, W> L(P, s_blob, b / W, b % W);
+  if (kPhased && L.is(I_PHASE) != kPhInner) return;
   const int zsel = L.is(I_ZSEL);
   const double penalty = L.sc(S_PENALTY);
   const double* zc = L.z(zsel, k);
@@ -1060,8 +1152,10 @@ __global__ void __launch_bounds__(128) k_update_expansions(SolverParams P) {
   for (int q = 0; q < n; ++q) e[(f++) * W] = lx[q];
   ALTRO_UNROLL
   for (int q = 0; q < m; ++q) e[(f++) * W] = lu[q];
-  // costs_(k) = Cost(x,u), ilqr.hpp:675
-  *L.costs(k) = knot_cost<n, m, W>(L.D, k, x, u, lam, penalty, nullptr);
+  if (!kPhased) {
+    // costs_(k) = Cost(x,u), ilqr.hpp:675
+    *L.costs(k) = knot_cost<n, m, W>(L.D, k, x, u, lam, AlPen(penalty), nullptr);
+  }
   if (k == 0) L.sc(S_CSRC_ALPHA) = -1.0;
 }
 
@@ -1129,7 +1223,10 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 // a kStages-deep shared-memory ring by TMA bulk copies (one per tile per knot) issued by lane 0
 // and tracked with mbarriers; every lane then reads its own column (conflict-free) and runs the
 // Riccati step in registers.  Writes K, d (and P, p when kStoreCtg).
-template <class M, int W, int kStages, bool kStoreCtg>
+// kPhased: only instances in kPhInner run; additionally hands sum_k max_i |d_i|/(|u_i|+1) and
+// the entry regularisation to the line-search kernels and lists the instances whose previous
+// search failed completely for k_ls_deep (phased.cuh).
+template <class M, int W, int kStages, bool kStoreCtg, bool kPhased = false>
 __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
   constexpr int n = M::n, m = M::m, nexp = Lane<M, W>::nexp, TPW = kWarp / W;
   constexpr uint32_t kRecBytes = nexp * W * sizeof(double);       // one tile's record
@@ -1143,7 +1240,10 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
   const Lane<M, W> L(P, nullptr, tile0 + lane / W, lane % W);    // a == 0 for every lane
   const DevOptions& o = P.opt;
   const int N = P.N;
-  const bool valid = L.valid;
+  const bool valid = L.valid && (!kPhased || L.is(I_PHASE) == kPhInner);
+  if (kPhased && !__any_sync(kFull, valid)) return;
+  const int zsel = (kPhased && valid) ? L.is(I_ZSEL) : 0;
+  double gs = 0.0;
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1165,10 +1265,12 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
     dreg = L.sc(S_DREG);
     st = L.is(I_STATUS);
   }
+  const double reg_in = reg, dreg_in = dreg;
   int max_reg_count = 0;
   bool repeat = valid;
   uint32_t issued = 0, consumed = 0;  // monotonically increasing slot counters (warp-uniform)
   while (__any_sync(kFull, repeat)) {
+    gs = 0.0;
     // terminal cost-to-go: lxx, lx of knot N (plain loads, once per pass)
     double Pm[n * n], p[n];
     {
@@ -1218,7 +1320,12 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
         ++issued;
       }
       if (live) {
-        double K[m * n], d[m];
+        double K[m * n], d[m], uk[m];
+        if (kPhased) {
+          const double* zc = L.z(zsel, k);
+          ALTRO_UNROLL
+          for (int q = 0; q < m; ++q) uk[q] = zc[(n + q) * W];
+        }
         const bool ok =
             riccati_step<n, m>(A, B, lxx, lxu, luu, lx, lu, Pm, p, reg, K, d, &dV0, &dV1);
         if (!ok) {  // ilqr.hpp:409-427: raise the regularisation, restart from k = N-1
@@ -1235,6 +1342,12 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
           for (int q = 0; q < m * n; ++q) pk[q * W] = K[q];
           ALTRO_UNROLL
           for (int q = 0; q < m; ++q) pk[(m * n + q) * W] = d[q];
+          if (kPhased) {
+            double g = fabs(d[0]) / (fabs(uk[0]) + 1);
+            ALTRO_UNROLL
+            for (int q = 1; q < m; ++q) g = fmax(g, fabs(d[q]) / (fabs(uk[q]) + 1));
+            gs += g;
+          }
           if (kStoreCtg) {
             double* c = L.ctg(k);
             ALTRO_UNROLL
@@ -1254,6 +1367,12 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
     L.sc(S_DV0) = dV0;
     L.sc(S_DV1) = dV1;
     L.is(I_STATUS) = st;
+    if (kPhased) {
+      L.sc(S_GS_BWD) = gs;
+      L.sc(S_REG_IN) = reg_in;
+      L.sc(S_DREG_IN) = dreg_in;
+      if (L.is(I_LSFAIL) != 0) P.list[atomicAdd(&P.counters[3], 1)] = L.b << 1;
+    }
   }
 }
 

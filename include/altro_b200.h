@@ -74,7 +74,8 @@ typedef struct altro_b200_options {
   int32_t check_forwardpass_bounds;
   int32_t line_search_max_iterations;
   int32_t reset_duals;
-  int32_t _pad;
+  int32_t skip_repeated_iterations; /* extension, default 0: account for provably identical repeated
+                                       inner iterations without executing them (same results) */
   double cost_tolerance;
   double gradient_tolerance;
   double bp_reg_increase_factor;
@@ -164,8 +165,21 @@ int altro_b200_solver_set_penalty(altro_b200_solver* s, double rho, void* stream
 int altro_b200_solver_set_duals_host(altro_b200_solver* s, int k, const double* lambda, int p,
                                      void* stream);
 
+/* --- execution engine -----------------------------------------------------------------
+ * Both engines run the same per-instance arithmetic and return the same results.
+ *  FUSED : one persistent warp-per-tile kernel (k_solve) runs whole solves.
+ *  PHASED: every inner iteration of the batch is UpdateExpansions -> BackwardPass (TMA-streamed
+ *          over the materialised expansions, the reference's data flow ilqr.hpp:300-313) ->
+ *          ForwardPass kernels, each with its own thread mapping; default for n <= 6.
+ * The engine is fixed when a solver is created: altro_b200_set_default_engine() (process-wide),
+ * else the environment variable ALTRO_B200_ENGINE=fused|phased, else PHASED. */
+#define ALTRO_B200_ENGINE_FUSED 0
+#define ALTRO_B200_ENGINE_PHASED 1
+void altro_b200_set_default_engine(int engine);
+int altro_b200_solver_engine(const altro_b200_solver* s);
+
 /* --- whole solves, device resident, no host round trip -------------------------------
- * AugmentedLagrangianiLQR::Solve(), al_solver.hpp:304-334 (one fused persistent kernel) */
+ * AugmentedLagrangianiLQR::Solve(), al_solver.hpp:304-334 */
 int altro_b200_solve_al(altro_b200_solver* s, void* stream);
 /* iLQR::Solve(), ilqr.hpp:284-316 */
 int altro_b200_solve_ilqr(altro_b200_solver* s, void* stream);
@@ -242,6 +256,8 @@ int altro_b200_get_scalars_host(altro_b200_solver* s, double* reg, double* dV0, 
 size_t altro_b200_backward_pass_bytes(const altro_b200_solver* s);
 /* number of kernels this library has launched on behalf of `s` since creation */
 int64_t altro_b200_kernel_launches(const altro_b200_solver* s);
+/* latency probe: cycles per call of the per-knot device functions on one warp (cycles[16]) */
+int altro_b200_microbench(altro_b200_solver* s, long long* cycles, int reps);
 /* device bytes held by the solver */
 size_t altro_b200_device_bytes(const altro_b200_solver* s);
 
