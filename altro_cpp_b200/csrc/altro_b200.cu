@@ -6,11 +6,13 @@
 // fallback — without a usable CUDA device every compute entry point fails.
 #include "../../include/altro_b200.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <string>
 #include <vector>
@@ -96,7 +98,16 @@ int build_blob(const altro_b200_problem& p, bool use_constraints, std::vector<ch
       pmax = std::max(pmax, row);
       for (int bi = 0; bi < cs.nblocks; ++bi) {
         const ConBlock& c = cs.blk[bi];
-        cs.hdr[bi] = make_int4(c.kind | (c.equality << 8) | (c.p << 16), c.row0, c.nl, c.xi | (c.yi << 8));
+        int shape = kShapeGeneric;
+        if (c.kind == kControlBound && c.nl == m && c.nu == m && c.p == 2 * m) {
+          bool canonical = true;
+          for (int i = 0; i < 2 * m; ++i) canonical = canonical && c.idx[i] == i % m;
+          if (canonical) shape = kShapeBoundsFull;
+        } else if (c.kind == kCircle && c.p <= 4) {
+          shape = kShapeCirclesOneChunk;
+        }
+        cs.hdr[bi] = make_int4(c.kind | (c.equality << 8) | (shape << 12) | (c.p << 16), c.row0, c.nl,
+                               c.xi | (c.yi << 8));
       }
     }
     int id = -1;
@@ -166,11 +177,15 @@ struct Ops {
   cudaError_t (*ls_wide)(const SolverParams&, int mode, cudaStream_t) = nullptr;
   cudaError_t (*ls_deep)(const SolverParams&, int mode, int max_instances, cudaStream_t) = nullptr;
   cudaError_t (*microbench)(const SolverParams&, double* sink, long long* out, int reps, cudaStream_t) = nullptr;
+  // split line search: rollout / per-knot cost / acceptance kernels (wide: all tiles; deep: the list)
+  cudaError_t (*ls_split_wide)(const SolverParams&, int mode, cudaStream_t) = nullptr;
+  cudaError_t (*ls_split_deep)(const SolverParams&, int mode, int max_instances, cudaStream_t) = nullptr;
   bool large = false;  // one instance per CTA (large.cuh): whole solves only, W = 1 layout
 };
 
 constexpr int kBpStages = 4;
 constexpr int kPhasedTile = 8;  // tile width of the phased engine's workspaces
+constexpr int kCostGrid = 148 * 12;  // persistent CTAs of the per-knot cost kernels
 
 template <class M, int W>
 int solve_smem(const SolverParams& P) {
@@ -196,7 +211,7 @@ Ops make_ops() {
   };
   o.expansions = [](const SolverParams& P, cudaStream_t st) -> cudaError_t {
     dim3 grid((P.B + 127) / 128, P.N + 1);
-    k_update_expansions<M, W><<<grid, 128, P.blob_bytes, st>>>(P);
+    k_update_expansions<M, W><<<grid, 128, 0, st>>>(P);
     return cudaGetLastError();
   };
   o.con_values = [](const SolverParams& P, int k, double* out, cudaStream_t st) -> cudaError_t {
@@ -227,7 +242,7 @@ Ops make_ops() {
     };
     o.expansions_phased = [](const SolverParams& P, cudaStream_t st) -> cudaError_t {
       dim3 grid((P.B + 127) / 128, P.N + 1);
-      k_update_expansions<M, W, true><<<grid, 128, P.blob_bytes, st>>>(P);
+      k_update_expansions<M, W, true><<<grid, 128, 0, st>>>(P);
       return cudaGetLastError();
     };
     o.backward_phased = [](const SolverParams& P, cudaStream_t st) -> cudaError_t {
@@ -237,6 +252,36 @@ Ops make_ops() {
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return e;
       k_backward_mat<M, W, kBpStages, false, true><<<grid, kWarp, smem, st>>>(P);
+      return cudaGetLastError();
+    };
+    o.ls_split_wide = [](const SolverParams& P, int mode, cudaStream_t st) -> cudaError_t {
+      const int blob = ((P.blob_bytes + 15) / 16) * 16;
+      const int smem_roll = blob + kLsWarps * p_roll_stage_doubles<M>(W) * sizeof(double);
+      const int smem_acc = kLsWarps * W * P.N * sizeof(double);
+      cudaError_t e = cudaFuncSetAttribute(k_roll_wide<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(k_acc_wide<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_acc);
+      if (e != cudaSuccess) return e;
+      const int grid = (P.T + kLsWarps - 1) / kLsWarps;
+      k_roll_wide<M, W><<<grid, kLsWarps * kWarp, smem_roll, st>>>(P);
+      const long items = static_cast<long>(P.T) * (P.N + 1);
+      const int cgrid = static_cast<int>(std::min<long>((items + kLsWarps - 1) / kLsWarps, kCostGrid));
+      k_cost_wide<M, W><<<cgrid, kLsWarps * kWarp, P.blob_bytes, st>>>(P);
+      k_acc_wide<M, W><<<grid, kLsWarps * kWarp, smem_acc, st>>>(P, mode);
+      return cudaGetLastError();
+    };
+    o.ls_split_deep = [](const SolverParams& P, int mode, int max_instances, cudaStream_t st) -> cudaError_t {
+      const int blob = ((P.blob_bytes + 15) / 16) * 16;
+      const int smem_roll = blob + kLsWarps * p_roll_stage_doubles<M>(1) * sizeof(double);
+      const int smem_acc = kLsWarps * P.N * sizeof(double);
+      cudaError_t e = cudaFuncSetAttribute(k_roll_deep<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll);
+      if (e != cudaSuccess) return e;
+      const int grid = (max_instances + kLsWarps - 1) / kLsWarps;
+      k_roll_deep<M, W><<<grid, kLsWarps * kWarp, smem_roll, st>>>(P, kWarp / W);
+      const long items = static_cast<long>(max_instances) * (P.N + 1);
+      const int cgrid = static_cast<int>(std::min<long>((items + kLsWarps - 1) / kLsWarps, kCostGrid));
+      k_cost_deep<M, W><<<cgrid, kLsWarps * kWarp, P.blob_bytes, st>>>(P, kWarp / W);
+      k_acc_deep<M, W><<<grid, kLsWarps * kWarp, smem_acc, st>>>(P, mode, kWarp / W);
       return cudaGetLastError();
     };
     o.ls_wide = [](const SolverParams& P, int mode, cudaStream_t st) -> cudaError_t {
@@ -384,6 +429,10 @@ struct altro_b200_solver {
       if ((rc = alloc(reinterpret_cast<void**>(&P.CAND), bytes))) return rc;
     }
     if (!P.list && (rc = alloc(reinterpret_cast<void**>(&P.list), static_cast<size_t>(Bp) * sizeof(int)))) return rc;
+    if (!P.COSTK) {
+      if ((rc = alloc(reinterpret_cast<void**>(&P.COSTK), static_cast<size_t>(N + 1) * Bp * kWarp * sizeof(double)))) return rc;
+      if ((rc = alloc(reinterpret_cast<void**>(&P.TRYST), static_cast<size_t>(Bp) * kWarp * sizeof(int)))) return rc;
+    }
     return 0;
   }
   int ensure_stepwise() {  // EXP / CTG / COSTS are only needed by the step-wise API
@@ -417,6 +466,19 @@ struct DeviceGuard {
   }
 };
 
+// Largest double t with sqrt(t) <= mx, so that `sqrt(s) > mx` and `s > t` are the same predicate
+// for every s >= 0 (sqrt is monotone and correctly rounded on host and device alike).
+double sqrt_threshold(double mx) {
+  if (std::isnan(mx)) return std::numeric_limits<double>::quiet_NaN();  // sqrt(s) > NaN is never true
+  if (mx < 0) return -1.0;                                              // always true for s >= 0
+  if (std::isinf(mx)) return mx;
+  double t = mx * mx;
+  if (std::isinf(t)) return std::numeric_limits<double>::max();
+  while (std::sqrt(t) > mx) t = std::nextafter(t, 0.0);
+  while (std::sqrt(std::nextafter(t, HUGE_VAL)) <= mx) t = std::nextafter(t, HUGE_VAL);
+  return t;
+}
+
 DevOptions to_dev(const altro_b200_options& o) {
   DevOptions d;
   std::memset(&d, 0, sizeof(d));
@@ -436,6 +498,8 @@ DevOptions to_dev(const altro_b200_options& o) {
   d.bp_reg_min = o.bp_reg_min;
   d.state_max = o.state_max;
   d.control_max = o.control_max;
+  d.state_max_sq = sqrt_threshold(o.state_max);
+  d.control_max_sq = sqrt_threshold(o.control_max);
   d.line_search_lower_bound = o.line_search_lower_bound;
   d.line_search_upper_bound = o.line_search_upper_bound;
   d.line_search_decrease_factor = o.line_search_decrease_factor;
@@ -969,6 +1033,12 @@ static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
     CU(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
   }
   const int lsmode = mode | (overlap ? 2 : 0);
+  // the split line search evaluates the tries in two rounds (32/W, then 32): longer searches use
+  // the fused line-search kernels, which loop
+  // ... and only pays when few instances are in flight (the slot is then bound by the length of
+  // the serial chains, not by instruction throughput)
+  const int split_max = env_int("ALTRO_B200_SPLIT_MAX", 2048);
+  const bool split_ok = s->P.opt.line_search_max_iterations <= kWarp / kPhasedTile + kWarp;
   for (long slot = 0; slot < 10000000; ++slot) {
     cur->opt = s->P.opt;
     CU(cudaMemsetAsync(cur->counters, 0, 8 * sizeof(int), st));
@@ -989,8 +1059,14 @@ static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
     }
     PH(cur_ops.expansions_phased(*cur, st), "k_update_expansions");
     PH(cur_ops.backward_phased(*cur, st), "k_backward_mat");
-    PH(cur_ops.ls_wide(*cur, lsmode, st), "k_ls_wide");
-    PH(cur_ops.ls_deep(*cur, lsmode, cur->B, st), "k_ls_deep");
+    if (split_ok && cur->B <= split_max) {
+      PH(cur_ops.ls_split_wide(*cur, lsmode, st), "k_roll/cost/acc_wide");
+      PH(cur_ops.ls_split_deep(*cur, lsmode, cur->B, st), "k_roll/cost/acc_deep");
+      s->launches += 4;
+    } else {
+      PH(cur_ops.ls_wide(*cur, lsmode, st), "k_ls_wide");
+      PH(cur_ops.ls_deep(*cur, lsmode, cur->B, st), "k_ls_deep");
+    }
     if (overlap) CU(cudaStreamWaitEvent(st, s->ev_join, 0));
     if (!polling) continue;
     CU(cudaStreamSynchronize(st));
@@ -1012,6 +1088,7 @@ static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
       Q.N = s->N; Q.n = s->n; Q.m = s->m; Q.pmax = s->pmax; Q.use_al = s->use_al;
       Q.blob = s->P.blob; Q.blob_bytes = s->P.blob_bytes;
       Q.EXP = s->P.EXP; Q.CAND = s->P.CAND; Q.list = s->P.list;  // per-slot scratch, shared
+      Q.COSTK = s->P.COSTK; Q.TRYST = s->P.TRYST;
       lookup_ops(s->n, s->m, s->model, Q.W, &w.ops);
       dim3 grid((unfinished + 127) / 128, s->N + 2);
       k_move_instances<<<grid, 128, 0, st>>>(*cur, Q, s->d_list, unfinished, 0);
@@ -1039,14 +1116,18 @@ int altro_b200_solve_ilqr(altro_b200_solver* s, void* stream) { return solve_dis
 int altro_b200_microbench(altro_b200_solver* s, long long* cycles, int reps) {
   if (!s || !cycles || !s->ops.microbench) return fail(ALTRO_B200_ERR_UNSUPPORTED, "microbench: unsupported solver");
   DeviceGuard guard(s->device);
+  {
+    int rc = s->ensure_phased();
+    if (rc) return rc;
+  }
   double* sink = nullptr;
   long long* out = nullptr;
   CU(cudaMalloc(&sink, 32 * sizeof(double)));
-  CU(cudaMalloc(&out, 16 * sizeof(long long)));
-  CU(cudaMemset(out, 0, 16 * sizeof(long long)));
+  CU(cudaMalloc(&out, 32 * sizeof(long long)));
+  CU(cudaMemset(out, 0, 32 * sizeof(long long)));
   cudaError_t e = s->ops.microbench(s->P, sink, out, reps, 0);
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  if (e == cudaSuccess) e = cudaMemcpy(cycles, out, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(cycles, out, 32 * sizeof(long long), cudaMemcpyDeviceToHost);
   cudaFree(sink);
   cudaFree(out);
   if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("microbench: ") + cudaGetErrorString(e));

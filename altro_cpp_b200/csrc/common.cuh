@@ -45,6 +45,14 @@ enum Status : int {
   kBackwardPassRegularizationFailed = 9,
 };
 
+// Shapes of a constraint block the device code has straight-line paths for (same arithmetic as the
+// generic row loop, fewer instructions); detected when the blob is built.
+enum BlockShape : int {
+  kShapeGeneric = 0,
+  kShapeBoundsFull = 1,        // control bound with finite lower and upper bounds on every control
+  kShapeCirclesOneChunk = 2,   // circle block with at most 4 circles
+};
+
 // One ConstraintValues<n,m,ConType> (altro/constraints/constraint_values.hpp:24) of a knot.
 struct ConBlock {
   int kind;      // ConKind
@@ -66,7 +74,7 @@ struct ConSet {
   int p_total;
   int _pad[2];
   // packed copy of the scalar fields of blk[i], one 16-byte load per block:
-  // x = kind | equality << 8 | p << 16, y = row0, z = nl, w = xi | yi << 8
+  // x = kind | equality << 8 | shape << 12 | p << 16, y = row0, z = nl, w = xi | yi << 8
   int4 hdr[kMaxBlocks];
   ConBlock blk[kMaxBlocks];
 };
@@ -133,6 +141,8 @@ struct DevOptions {
   double cost_tolerance, gradient_tolerance;
   double bp_reg_increase_factor, bp_reg_initial, bp_reg_max, bp_reg_min;
   double state_max, control_max;
+  // largest t with sqrt(t) <= state_max / control_max: `sqrt(s) > max` is `s > t` (ilqr.hpp:484-495)
+  double state_max_sq, control_max_sq;
   double line_search_lower_bound, line_search_upper_bound, line_search_decrease_factor;
   double constraint_tolerance, maximum_penalty, initial_penalty, penalty_scaling;
 };
@@ -204,6 +214,9 @@ struct SolverParams {
                   // cursors; [3] = entries of `list` (phased engine); 8 ints
   int* list;      // [Bp] phased engine: instances whose line search continues in k_ls_deep
   double* CAND;   // [Bp][N+1][n+m][32]  phased engine: candidate trajectories of k_ls_deep (scratch)
+  double* COSTK;  // [Bp][N+1][32]  phased engine: per-knot costs of line-search candidates (scratch),
+                  //                row = tile (wide kernels) or list entry (deep kernels), lane fastest
+  int* TRYST;     // [Bp][32]       phased engine: status left by each candidate rollout
   DevOptions opt;
 };
 

@@ -60,6 +60,10 @@ __device__ __forceinline__ void mattmul(const double* A, const double* B, double
 struct Unicycle {  // examples/unicycle.cpp:12-33
   static constexpr int n = 3, m = 2;
   static constexpr bool kDiscrete = false;
+  // xdot depends on the state only through x[2] and xdot[2] = u[1] does not depend on the state:
+  // RK4 stages 2 and 3 are evaluated at bitwise the same x[2], so k3 == k2 (and the stage
+  // Jacobians coincide) — one sin/cos pair less per step with identical results
+  static constexpr bool kStage3RepeatsStage2 = true;
   // value and Jacobian at the same point share one sin/cos evaluation (same results)
   static __device__ __forceinline__ void eval_jac(const double*, const double* x, const double* u,
                                                   double* xd, double* A, double* B) {
@@ -106,6 +110,7 @@ template <int dof>
 struct TripleIntegrator {  // examples/triple_integrator.cpp:9-33
   static constexpr int n = 3 * dof, m = dof;
   static constexpr bool kDiscrete = false;
+  static constexpr bool kStage3RepeatsStage2 = false;
   static __device__ __forceinline__ void eval(const double*, const double* x, const double* u,
                                               double* xd) {
     ALTRO_UNROLL
@@ -133,6 +138,7 @@ struct TripleIntegrator {  // examples/triple_integrator.cpp:9-33
 struct Cartpole {  // definition owned by this repo; oracle: altro_oracle.hpp ModelEvaluate
   static constexpr int n = 4, m = 1;
   static constexpr bool kDiscrete = false;
+  static constexpr bool kStage3RepeatsStage2 = false;
   static __device__ __forceinline__ void eval(const double* P, const double* x, const double* u,
                                               double* xd) {
     const double mc = P[0], mp = P[1], l = P[2], g = P[3];
@@ -202,13 +208,17 @@ __device__ __forceinline__ void rk4_step(const double* P, const double* x, const
   ALTRO_UNROLL
   for (int i = 0; i < n; ++i) xt[i] = x[i] + k1[i] * 0.5 * h;
   M::eval(P, xt, u, k2);
-  ALTRO_UNROLL
-  for (int i = 0; i < n; ++i) xt[i] = x[i] + k2[i] * 0.5 * h;
-  M::eval(P, xt, u, k3);
+  if (M::kStage3RepeatsStage2) {
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) k3[i] = k2[i];
+  } else {
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) xt[i] = x[i] + k2[i] * 0.5 * h;
+    M::eval(P, xt, u, k3);
+  }
   ALTRO_UNROLL
   for (int i = 0; i < n; ++i) xt[i] = x[i] + k3[i] * h;
   M::eval(P, xt, u, k4);
-  ALTRO_UNROLL
   const double r6 = 1.0 / 6.0;
   ALTRO_UNROLL
   for (int i = 0; i < n; ++i) xn[i] = x[i] + div_by(h * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]), 6.0, r6);
@@ -245,9 +255,14 @@ __device__ __forceinline__ void rk4_jacobian(const double* P, const double* x, c
   ALTRO_UNROLL
   for (int i = 0; i < n * m; ++i) { dB[i] = Bs[i] * h + TB[i] * h; B[i] = B[i] + 2 * dB[i]; }
   // stage 2: x + 0.5*k2*h
-  ALTRO_UNROLL
-  for (int i = 0; i < n; ++i) xt[i] = x[i] + k2[i] * 0.5 * h;
-  EvalJac<M>::run(P, xt, u, k3, As, Bs);
+  if (M::kStage3RepeatsStage2) {  // same point as stage 1: As, Bs stay, k3 = k2
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) k3[i] = k2[i];
+  } else {
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) xt[i] = x[i] + k2[i] * 0.5 * h;
+    EvalJac<M>::run(P, xt, u, k3, As, Bs);
+  }
   ALTRO_UNROLL
   for (int j = 0; j < n; ++j)
     ALTRO_UNROLL
@@ -401,10 +416,11 @@ constexpr int kChunk = 4;
 
 // scalar fields of a constraint block, unpacked from ConSet::hdr (one 16-byte load)
 struct BlockHdr {
-  int kind, p, row0, nl, xi, yi;
+  int kind, p, row0, nl, xi, yi, shape;
   bool eq;
   __device__ __forceinline__ explicit BlockHdr(const int4& h)
-      : kind(h.x & 0xff), p(h.x >> 16), row0(h.y), nl(h.z), xi(h.w & 0xff), yi(h.w >> 8), eq(((h.x >> 8) & 1) != 0) {}
+      : kind(h.x & 0xff), p(h.x >> 16), row0(h.y), nl(h.z), xi(h.w & 0xff), yi(h.w >> 8),
+        shape((h.x >> 12) & 0xf), eq(((h.x >> 8) & 1) != 0) {}
 };
 
 // penalty and the reciprocal used by `/ (2 rho)` (constraint_values.hpp:118), computed once per sweep
@@ -417,7 +433,38 @@ template <int n, int m, class F>
 __device__ __forceinline__ void for_row_chunks(const BlockHdr& hd, const ConBlock& b, const double* x,
                                                const double* u, F&& f) {
   const int p = hd.p;
-  if (hd.kind == kCircle) {
+  if (hd.shape == kShapeBoundsFull) {
+    // every control has a finite lower and upper bound: rows j < m are lb_j - u_j, rows m + j are
+    // u_j - ub_j; everything but the bound values is known at compile time
+    ALTRO_UNROLL
+    for (int r0 = 0; r0 < 2 * m; r0 += kChunk) {
+      double c[kChunk];
+      int ic[kChunk];
+      bool ok[kChunk];
+      ALTRO_UNROLL
+      for (int q = 0; q < kChunk; ++q) {
+        const int r = r0 + q;
+        ok[q] = r < 2 * m;
+        ic[q] = ok[q] ? r : 2 * m - 1;
+        const double uj = u[ic[q] % m];
+        c[q] = (ic[q] < m) ? (b.a[ic[q]] - uj) : (uj - b.a[ic[q]]);
+      }
+      f(c, ic, ok);
+    }
+  } else if (hd.shape == kShapeCirclesOneChunk) {
+    const double px = pick<n>(x, hd.xi), py = pick<n>(x, hd.yi);
+    double c[kChunk];
+    int ic[kChunk];
+    bool ok[kChunk];
+    ALTRO_UNROLL
+    for (int q = 0; q < kChunk; ++q) {
+      ok[q] = q < p;
+      ic[q] = ok[q] ? q : p - 1;
+      const double dx = px - b.a[q], dy = py - b.b[q];  // rows past p: zero-filled, masked by f
+      c[q] = -(dx * dx + dy * dy - b.c[q] * b.c[q]);
+    }
+    f(c, ic, ok);
+  } else if (hd.kind == kCircle) {
     const double px = pick<n>(x, hd.xi), py = pick<n>(x, hd.yi);
     for (int r0 = 0; r0 < p; r0 += kChunk) {
       double c[kChunk];

@@ -205,10 +205,10 @@ __device__ __forceinline__ bool sweep_forward(const Lane<M, W>& L, double* stg, 
           for (int q = 0; q < n; ++q) sx += x[q] * x[q];
           ALTRO_UNROLL
           for (int q = 0; q < m; ++q) su += u[q] * u[q];
-          if (sqrt(sx) > o.state_max) {
+          if (sx > o.state_max_sq) {  // sqrt(sx) > state_max, see DevOptions
             status = kStateLimit;
             ok = false;
-          } else if (sqrt(su) > o.control_max) {
+          } else if (su > o.control_max_sq) {
             status = kControlLimit;
             ok = false;
           }
@@ -1107,10 +1107,14 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp) k_phase(SolverParams P, in
 // thread-pool tasks (ilqr.hpp:354-365) but with the batch as the wide axis.
 // kPhased: only instances about to run an inner iteration (kPhInner) are expanded and the
 // per-knot costs_ are not stored (the phased engine carries J0 like k_solve does).
+#ifndef ALTRO_EXP_MINB
+#define ALTRO_EXP_MINB 4
+#endif
 template <class M, int W, bool kPhased = false>
-__global__ void __launch_bounds__(128) k_update_expansions(SolverParams P) {
-  extern __shared__ __align__(128) char s_blob[];
-  copy_blob(P.blob, s_blob, P.blob_bytes);
+__global__ void __launch_bounds__(128, ALTRO_EXP_MINB) k_update_expansions(SolverParams P) {
+  // all threads of a CTA work on one knot: descriptor words are read from the global blob
+  // (uniform addresses, L1-resident); no per-CTA staging of the whole blob
+  const char* s_blob = P.blob;
   constexpr int n = M::n, m = M::m;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   const int k = blockIdx.y;
@@ -1293,6 +1297,14 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
     for (int s = 0; s < kStages && next_k >= 0; ++s, --next_k, ++issued)
       if (lane == 0) load_slot(issued % kStages, next_k);
     bool live = repeat;  // lanes still descending in this pass
+    double uk_next[m];
+    ALTRO_UNROLL
+    for (int q = 0; q < m; ++q) uk_next[q] = 0.0;
+    if (kPhased && live) {
+      const double* zc = L.z(zsel, N - 1);
+      ALTRO_UNROLL
+      for (int q = 0; q < m; ++q) uk_next[q] = zc[(n + q) * W];
+    }
     for (int k = N - 1; k >= 0; --k, ++consumed) {
       const int slot = consumed % kStages;
       mbar_wait(&bars[slot], (consumed / kStages) & 1);
@@ -1321,10 +1333,14 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
       }
       if (live) {
         double K[m * n], d[m], uk[m];
-        if (kPhased) {
-          const double* zc = L.z(zsel, k);
+        if (kPhased) {  // controls of this knot were requested one knot ago; request the next ones
           ALTRO_UNROLL
-          for (int q = 0; q < m; ++q) uk[q] = zc[(n + q) * W];
+          for (int q = 0; q < m; ++q) uk[q] = uk_next[q];
+          if (k > 0) {
+            const double* zc = L.z(zsel, k - 1);
+            ALTRO_UNROLL
+            for (int q = 0; q < m; ++q) uk_next[q] = zc[(n + q) * W];
+          }
         }
         const bool ok =
             riccati_step<n, m>(A, B, lxx, lxu, luu, lx, lu, Pm, p, reg, K, d, &dV0, &dV1);

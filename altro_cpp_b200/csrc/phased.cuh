@@ -63,7 +63,9 @@ __host__ __device__ constexpr int p_stage_doubles(int pmax, int WI) {
 // RolloutClosedLoop(alpha) + Cost(Zbar) + normalised feed-forward gain of the candidate
 // (ilqr.hpp:468-499, 326-334, 662-668).  The candidate is written to zo[k*zknot + f*zrow].
 // Returns false when the state/control bound check trips (status is set like the reference).
-template <class M, int W, int WI>
+// kDbg (latency probe only, 0 in every solve kernel): 1 no cost, 2 no dynamics, 4 no staging
+// after knot 0, 8 no candidate stores, 16 no normalised-gain division
+template <class M, int W, int WI, int kDbg = 0>
 __device__ __forceinline__ bool p_rollout(const PLane<M, W, WI>& L, double* stg, bool active, int zsel,
                                           double* zo, int zrow, int zknot, double alpha, double penalty,
                                           double& J, double& gsum, int& status) {
@@ -120,8 +122,8 @@ __device__ __forceinline__ bool p_rollout(const PLane<M, W, WI>& L, double* stg,
   for (int k = 0; k <= N; ++k) {
     cp_async_wait_all();
     __syncwarp();
-    if (k < N) issue(k + 1);
-    const double* s = stg + (k & 1) * R * WI + L.si;
+    if (k < N && !(kDbg & 4)) issue(k + 1);
+    const double* s = stg + ((kDbg & 4) ? 0 : (k & 1)) * R * WI + L.si;
     if (ok) {
       double* zn = zo + static_cast<size_t>(k) * zknot;
       double g = 0.0;
@@ -136,23 +138,31 @@ __device__ __forceinline__ bool p_rollout(const PLane<M, W, WI>& L, double* stg,
           for (int j = 1; j < n; ++j) acc += s[(nz + q + j * m) * WI] * dx[j];
           const double dq = s[(nz + m * n + q) * WI];
           u[q] = s[(n + q) * WI] + acc + dq * alpha;  // ilqr.hpp:478
-          const double gq = fabs(dq) / (fabs(u[q]) + 1);
+          const double gq = (kDbg & 16) ? fabs(dq) : fabs(dq) / (fabs(u[q]) + 1);
           g = (q == 0) ? gq : fmax(g, gq);
         }
       } else {  // terminal knot of Zbar: u_N = 0 (SetZero, Q14)
         ALTRO_UNROLL
         for (int q = 0; q < m; ++q) u[q] = 0.0;
       }
-      ALTRO_UNROLL
-      for (int q = 0; q < n; ++q) zn[q * zrow] = x[q];
-      ALTRO_UNROLL
-      for (int q = 0; q < m; ++q) zn[(n + q) * zrow] = u[q];
+      if (!(kDbg & 8)) {
+        ALTRO_UNROLL
+        for (int q = 0; q < n; ++q) zn[q * zrow] = x[q];
+        ALTRO_UNROLL
+        for (int q = 0; q < m; ++q) zn[(n + q) * zrow] = u[q];
+      }
       double v;
-      Jsum += knot_cost<n, m, WI>(D, k, x, u, s + off_lam * WI, pen, &v);
+      if (!(kDbg & 1)) Jsum += knot_cost<n, m, WI>(D, k, x, u, s + off_lam * WI, pen, &v);
+      else Jsum += u[0];
       if (k < N) {
         gs += g;
         double xn[n];
-        rk4_step<M>(mp, x, u, D.h(k), xn);
+        if (!(kDbg & 2)) {
+          rk4_step<M>(mp, x, u, D.h(k), xn);
+        } else {
+          ALTRO_UNROLL
+          for (int q = 0; q < n; ++q) xn[q] = x[q] + 1e-3 * u[q % m];
+        }
         ALTRO_UNROLL
         for (int q = 0; q < n; ++q) x[q] = xn[q];
         if (o.check_forwardpass_bounds) {  // ilqr.hpp:484-495
@@ -161,10 +171,10 @@ __device__ __forceinline__ bool p_rollout(const PLane<M, W, WI>& L, double* stg,
           for (int q = 0; q < n; ++q) sx += x[q] * x[q];
           ALTRO_UNROLL
           for (int q = 0; q < m; ++q) su += u[q] * u[q];
-          if (sqrt(sx) > o.state_max) {
+          if (sx > o.state_max_sq) {  // sqrt(sx) > state_max, see DevOptions
             status = kStateLimit;
             ok = false;
-          } else if (sqrt(su) > o.control_max) {
+          } else if (su > o.control_max_sq) {
             status = kControlLimit;
             ok = false;
           }
@@ -307,6 +317,415 @@ __device__ __forceinline__ void p_finish(const LaneT& L, int mode, const PLsResu
   L.is(I_STATUS) = st;
   L.is(I_PHASE) = phase;
   L.is(I_LSFAIL) = lsfail;
+}
+
+// ------------------------------------------------------------------------------------------
+// Split line search (default): the serial part of a candidate — RolloutClosedLoop, a chain of
+// N feedback + RK4 steps — runs alone in k_roll_*; Cost(Zbar) is independent per knot and runs
+// as one thread per (candidate, knot) in k_cost_*; k_acc_* sums the knot costs in knot order
+// (the same sum the fused kernels form), applies the acceptance test and, for the winner only,
+// computes the normalised feed-forward gain.  Same arithmetic per candidate as k_ls_wide /
+// k_ls_deep, but the serial chain is ~2.3x shorter.
+// ------------------------------------------------------------------------------------------
+constexpr int kRollStages = 4;  // knots in flight in the staging ring of the rollout kernels
+
+template <class M>
+__host__ __device__ constexpr int p_roll_stage_doubles(int WI) {
+  return kRollStages * ((M::n + M::m) + (M::m * M::n + M::m)) * WI;
+}
+
+template <int NKeep>
+__device__ __forceinline__ void cp_async_wait_keep() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(NKeep) : "memory");
+}
+
+// RolloutClosedLoop(alpha) only (ilqr.hpp:468-499): candidate to zo[k*zknot + f*zrow].
+template <class M, int W, int WI>
+__device__ __forceinline__ bool p_rollout_only(const PLane<M, W, WI>& L, double* stg, bool active, int zsel,
+                                               double* zo, int zrow, int zknot, double alpha, int& status) {
+  constexpr int n = M::n, m = M::m, nz = n + m, nkd = PLane<M, W, WI>::nkd, R = nz + nkd, NS = kRollStages;
+  const int N = L.P.N;
+  const DevOptions& o = L.P.opt;
+  const Desc& D = L.D;
+  const double* mp = D.params();
+  auto issue = [&](int k) {
+    if (k <= N) {
+      double* s = stg + (k % NS) * R * WI;
+      if (WI == 1) {  // one instance per warp: lane r stages row r
+        const int r = L.a;
+        if (r < nz) cp_async8(s + r, L.z(zsel, k) + r * W);
+        else if (r < R && k < N) cp_async8(s + r, L.kd(k) + (r - nz) * W);
+      } else if (L.a == 0) {
+        s += L.si;
+        const double* g = L.z(zsel, k);
+        ALTRO_UNROLL
+        for (int r = 0; r < nz; ++r) cp_async8(s + r * WI, g + r * W);
+        if (k < N) {
+          g = L.kd(k);
+          ALTRO_UNROLL
+          for (int r = 0; r < nkd; ++r) cp_async8(s + (nz + r) * WI, g + r * W);
+        }
+      }
+    }
+    cp_async_commit();  // one group per knot, empty past the end, so the wait count stays uniform
+  };
+  static_assert(WI != 1 || R <= kWarp, "row-per-lane staging needs R <= 32");
+  __syncwarp();
+  ALTRO_UNROLL
+  for (int k = 0; k < NS - 1; ++k) issue(k);
+  double x[n], u[m];
+  {
+    const double* px0 = L.x0();
+    ALTRO_UNROLL
+    for (int q = 0; q < n; ++q) x[q] = px0[q * W];
+  }
+  bool ok = active;
+  for (int k = 0; k <= N; ++k) {
+    cp_async_wait_keep<NS - 2>();  // knot k has landed
+    __syncwarp();
+    issue(k + NS - 1);
+    const double* s = stg + (k % NS) * R * WI + L.si;
+    if (ok) {
+      double* zn = zo + static_cast<size_t>(k) * zknot;
+      if (k < N) {
+        double dx[n];
+        ALTRO_UNROLL
+        for (int q = 0; q < n; ++q) dx[q] = x[q] - s[q * WI];
+        ALTRO_UNROLL
+        for (int q = 0; q < m; ++q) {
+          double acc = s[(nz + q) * WI] * dx[0];
+          ALTRO_UNROLL
+          for (int j = 1; j < n; ++j) acc += s[(nz + q + j * m) * WI] * dx[j];
+          const double dq = s[(nz + m * n + q) * WI];
+          u[q] = s[(n + q) * WI] + acc + dq * alpha;  // ilqr.hpp:478
+        }
+      } else {  // terminal knot of Zbar: u_N = 0 (SetZero, Q14)
+        ALTRO_UNROLL
+        for (int q = 0; q < m; ++q) u[q] = 0.0;
+      }
+      ALTRO_UNROLL
+      for (int q = 0; q < n; ++q) zn[q * zrow] = x[q];
+      ALTRO_UNROLL
+      for (int q = 0; q < m; ++q) zn[(n + q) * zrow] = u[q];
+      if (k < N) {
+        double xn[n];
+        rk4_step<M>(mp, x, u, D.h(k), xn);
+        ALTRO_UNROLL
+        for (int q = 0; q < n; ++q) x[q] = xn[q];
+        if (o.check_forwardpass_bounds) {  // ilqr.hpp:484-495
+          double sx = 0.0, su = 0.0;
+          ALTRO_UNROLL
+          for (int q = 0; q < n; ++q) sx += x[q] * x[q];
+          ALTRO_UNROLL
+          for (int q = 0; q < m; ++q) su += u[q] * u[q];
+          if (sx > o.state_max_sq) {  // sqrt(sx) > state_max, see DevOptions
+            status = kStateLimit;
+            ok = false;
+          } else if (su > o.control_max_sq) {
+            status = kControlLimit;
+            ok = false;
+          }
+        }
+      }
+    }
+  }
+  cp_async_wait_all();
+  if (ok) status = kUnsolved;  // ilqr.hpp:497
+  return ok;
+}
+
+// step length of try t: 1 / factor^t by repeated division, like `alpha /= factor` (ilqr.hpp:553)
+__device__ __forceinline__ double try_alpha(const DevOptions& o, int t) {
+  double alpha = 1.0;
+  for (int j = 0; j < t; ++j) alpha /= o.line_search_decrease_factor;
+  return alpha;
+}
+
+// max_i |d_i| / (|u_i| + 1) of one knot (NormalizedFeedforwardGain, ilqr.hpp:662-668)
+template <int m>
+__device__ __forceinline__ double knot_gain(const double* d, int ds, const double* u, int us) {
+  double g = 0.0;
+  ALTRO_UNROLL
+  for (int q = 0; q < m; ++q) {
+    const double gq = fabs(d[q * ds]) / (fabs(u[q * us]) + 1);
+    g = (q == 0) ? gq : fmax(g, gq);
+  }
+  return g;
+}
+
+// Acceptance over the G candidates of every instance of the warp (tries done0 + a), given each
+// candidate's cost J and rollout outcome; same rules and tie-breaking as p_line_search.
+template <int WI>
+__device__ __forceinline__ PLsResult p_accept(const DevOptions& o, int si, int a, bool run, bool mine, bool ok,
+                                              double J, double alpha, int st_try, double J0, double dV0,
+                                              double dV1, int done0, int& status, double& csrc) {
+  constexpr int G = kWarp / WI;
+  PLsResult r;
+  r.success = false;
+  r.exhausted = false;
+  r.slot = 0;
+  r.J = J0;
+  r.alpha = 1.0;
+  r.z = -1.0;
+  r.gsum = 0.0;
+  double z = -1.0;
+  bool acc = false;
+  if (mine && ok) {
+    const double expected = -alpha * (dV0 + alpha * dV1);
+    if (expected > 0.0) z = (J0 - J) / expected;
+    acc = o.line_search_lower_bound <= z && z <= o.line_search_upper_bound && J < J0;
+  }
+  const unsigned accm = __ballot_sync(kFull, acc);
+  const unsigned okm = __ballot_sync(kFull, mine && ok);
+  const unsigned minem = __ballot_sync(kFull, mine);
+  int win = -1, last = -1, lastok = -1;
+  ALTRO_UNROLL
+  for (int g = G - 1; g >= 0; --g) {
+    const unsigned bit = 1u << (si + WI * g);
+    if (accm & bit) win = g;
+    if ((minem & bit) && last < 0) last = g;
+    if ((okm & bit) && lastok < 0) lastok = g;
+  }
+  const int src_win = si + WI * (win < 0 ? 0 : win);
+  const double Jw = __shfl_sync(kFull, J, src_win);
+  const double aw = __shfl_sync(kFull, alpha, src_win);
+  const double zw = __shfl_sync(kFull, z, src_win);
+  const int st_last = __shfl_sync(kFull, st_try, si + WI * (last < 0 ? 0 : last));
+  const double a_lastok = __shfl_sync(kFull, alpha, si + WI * (lastok < 0 ? 0 : lastok));
+  if (run) {
+    if (win >= 0) {
+      r.success = true;
+      r.slot = win;
+      r.J = Jw;
+      r.alpha = aw;
+      r.z = zw;
+      status = kUnsolved;  // the accepted rollout ran to the end (ilqr.hpp:497)
+    } else {
+      if (last >= 0) status = st_last;   // status_ left by the last executed rollout
+      if (lastok >= 0) csrc = a_lastok;  // Cost(*Zbar_) refreshed the stored constraint values (Q8)
+      r.exhausted = done0 + G >= o.line_search_max_iterations;
+    }
+  }
+  (void)a;
+  return r;
+}
+
+// --- wide: tries 0 .. G-1 of every instance whose previous search did not fail completely -----
+template <class M, int W>
+__global__ void __launch_bounds__(kLsWarps* kWarp) k_roll_wide(SolverParams P) {
+  extern __shared__ __align__(128) char smem[];
+  copy_blob(P.blob, smem, P.blob_bytes);
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int tile = blockIdx.x * kLsWarps + warp;
+  if (tile >= P.T) return;
+  using LaneT = PLane<M, W, W>;
+  constexpr int G = LaneT::G, nz = LaneT::nz;
+  double* stg = reinterpret_cast<double*>(smem + ((P.blob_bytes + 15) / 16) * 16) +
+                static_cast<size_t>(warp) * p_roll_stage_doubles<M>(W);
+  const int b = tile * W + lane % W;
+  const LaneT L(P, smem, b, lane / W, lane % W, b < P.B);
+  const bool run = L.valid && L.is(I_PHASE) == kPhInner && L.is(I_LSFAIL) == 0;
+  if (!__any_sync(kFull, run)) return;
+  const int zsel = run ? L.is(I_ZSEL) : 0;
+  int st_try = run ? L.is(I_STATUS) : kUnsolved;
+  const bool mine = run && L.a < P.opt.line_search_max_iterations;
+  const double alpha = try_alpha(P.opt, L.a);
+  double* zo = L.z((zsel + 1 + L.a) % (G + 1), 0);
+  p_rollout_only<M, W, W>(L, stg, mine, zsel, zo, W, nz * W, alpha, st_try);
+  if (mine) P.TRYST[tile * kWarp + lane] = st_try;
+}
+
+// ALCost::Evaluate (al_cost.hpp:264-274) of every knot of every candidate: a work item is one
+// (tile, knot) row of 32 lanes (lane = a*W + i, like the rollout and acceptance kernels); the
+// persistent CTAs walk the items with a grid stride, the problem blob is staged once per CTA.
+// COSTK[(tile*(N+1) + k)*32 + lane].
+template <class M, int W>
+__global__ void __launch_bounds__(kLsWarps* kWarp) k_cost_wide(SolverParams P) {
+  extern __shared__ __align__(128) char s_blob[];
+  copy_blob(P.blob, s_blob, P.blob_bytes);
+  constexpr int n = M::n, m = M::m, G = kWarp / W;
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int nk = P.N + 1;
+  const long items = static_cast<long>(P.T) * nk;
+  const int i = lane % W, a = lane / W;
+  for (long w = static_cast<long>(blockIdx.x) * kLsWarps + warp; w < items; w += static_cast<long>(gridDim.x) * kLsWarps) {
+    const int tile = static_cast<int>(w / nk), k = static_cast<int>(w % nk);
+    const int b = tile * W + i;
+    if (b >= P.B) continue;
+    const PLane<M, W, W> L(P, s_blob, b, a, i, true);
+    if (L.is(I_PHASE) != kPhInner || L.is(I_LSFAIL) != 0 || a >= P.opt.line_search_max_iterations) continue;
+    const int zsel = L.is(I_ZSEL);
+    const double* zc = L.z((zsel + 1 + a) % (G + 1), k);
+    double x[n], u[m];
+    ALTRO_UNROLL
+    for (int q = 0; q < n; ++q) x[q] = zc[q * W];
+    ALTRO_UNROLL
+    for (int q = 0; q < m; ++q) u[q] = zc[(n + q) * W];
+    const AlPen pen(L.sc(S_PENALTY));
+    const double* lam = P.pmax > 0 ? L.lam(k) : nullptr;
+    P.COSTK[static_cast<size_t>(w) * kWarp + lane] = knot_cost<n, m, W>(L.D, k, x, u, lam, pen, nullptr);
+  }
+}
+
+template <class M, int W>
+__global__ void __launch_bounds__(kLsWarps* kWarp) k_acc_wide(SolverParams P, int mode) {
+  extern __shared__ __align__(128) char smem[];  // per warp: W x N doubles for the winner's gains
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int tile = blockIdx.x * kLsWarps + warp;
+  if (tile >= P.T) return;
+  using LaneT = PLane<M, W, W>;
+  constexpr int G = LaneT::G, n = M::n, m = M::m;
+  const int N = P.N;
+  double* gbuf = reinterpret_cast<double*>(smem) + static_cast<size_t>(warp) * W * N;
+  const int b = tile * W + lane % W;
+  const LaneT L(P, nullptr, b, lane / W, lane % W, b < P.B);
+  const bool run = L.valid && L.is(I_PHASE) == kPhInner && L.is(I_LSFAIL) == 0;
+  if (!__any_sync(kFull, run)) return;
+  int zsel = 0, st = kUnsolved, st_try = kUnsolved;
+  double J0 = 0.0, dV0 = 0.0, dV1 = 0.0, csrc = -1.0;
+  const bool mine = run && L.a < P.opt.line_search_max_iterations;
+  if (run) {
+    zsel = L.is(I_ZSEL);
+    st = L.is(I_STATUS);
+    J0 = L.sc(S_J0);
+    dV0 = L.sc(S_DV0);
+    dV1 = L.sc(S_DV1);
+    csrc = L.sc(S_CSRC_ALPHA);
+  }
+  double J = 0.0;
+  if (mine) {
+    st_try = P.TRYST[tile * kWarp + lane];
+    const double* ck = P.COSTK + static_cast<size_t>(tile) * (N + 1) * kWarp + lane;
+    for (int k = 0; k <= N; ++k) J += ck[k * kWarp];  // Cost(): sum in knot order
+  }
+  const double alpha = try_alpha(P.opt, L.a);
+  PLsResult r = p_accept<W>(P.opt, L.si, L.a, run, mine, mine && st_try == kUnsolved, J, alpha, st_try, J0, dV0,
+                            dV1, 0, st, csrc);
+  // normalised feed-forward gain of the accepted candidate: its G lanes take the knots round-robin,
+  // the owner sums them in knot order
+  const bool succ = run && r.success;
+  if (__any_sync(kFull, succ)) {
+    if (succ) {
+      const int sel = (zsel + 1 + r.slot) % (G + 1);
+      for (int k = L.a; k < N; k += G) gbuf[L.si * N + k] = knot_gain<m>(L.kd(k) + m * n * W, W, L.z(sel, k) + n * W, W);
+    }
+    __syncwarp();
+    if (succ && L.a == 0) {
+      double gs = 0.0;
+      for (int k = 0; k < N; ++k) gs += gbuf[L.si * N + k];
+      r.gsum = gs;
+    }
+  }
+  if (run && L.a == 0) {
+    if (r.success || r.exhausted) {
+      p_finish(L, mode, r, (zsel + 1 + r.slot) % (G + 1), zsel, J0, csrc, st);
+    } else {  // continue with try G in the deep kernels
+      L.sc(S_CSRC_ALPHA) = csrc;
+      L.is(I_STATUS) = st;
+      P.list[atomicAdd(&P.counters[3], 1)] = (b << 1) | 1;
+    }
+  }
+}
+
+// --- deep: the next 32 tries of the instances on P.list, one instance per warp ------------------
+template <class M, int W>
+__global__ void __launch_bounds__(kLsWarps* kWarp) k_roll_deep(SolverParams P, int wide_tries) {
+  extern __shared__ __align__(128) char smem[];
+  const int count = P.counters[3];
+  if (static_cast<int>(blockIdx.x) * kLsWarps >= count) return;
+  copy_blob(P.blob, smem, P.blob_bytes);
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int j = blockIdx.x * kLsWarps + warp;
+  if (j >= count) return;
+  using LaneT = PLane<M, W, 1>;
+  constexpr int nz = LaneT::nz;
+  double* stg = reinterpret_cast<double*>(smem + ((P.blob_bytes + 15) / 16) * 16) +
+                static_cast<size_t>(warp) * p_roll_stage_doubles<M>(1);
+  const int entry = P.list[j];
+  const LaneT L(P, smem, entry >> 1, lane, 0, true);
+  const int t = ((entry & 1) ? wide_tries : 0) + lane;
+  const bool mine = t < P.opt.line_search_max_iterations;
+  int st_try = L.is(I_STATUS);
+  double* cand = P.CAND + static_cast<size_t>(j) * (P.N + 1) * nz * kWarp + lane;
+  p_rollout_only<M, W, 1>(L, stg, mine, L.is(I_ZSEL), cand, kWarp, nz * kWarp, try_alpha(P.opt, t), st_try);
+  if (mine) P.TRYST[j * kWarp + lane] = st_try;
+}
+
+// same for the candidates of k_roll_deep: item = (list entry j, knot), lane = try.
+// COSTK[(j*(N+1) + k)*32 + lane].
+template <class M, int W>
+__global__ void __launch_bounds__(kLsWarps* kWarp) k_cost_deep(SolverParams P, int wide_tries) {
+  extern __shared__ __align__(128) char s_blob[];
+  const int count = P.counters[3];
+  const int nk = P.N + 1;
+  const long items = static_cast<long>(count) * nk;
+  if (static_cast<long>(blockIdx.x) * kLsWarps >= items) return;
+  copy_blob(P.blob, s_blob, P.blob_bytes);
+  constexpr int n = M::n, m = M::m, nz = n + m;
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  for (long w = static_cast<long>(blockIdx.x) * kLsWarps + warp; w < items; w += static_cast<long>(gridDim.x) * kLsWarps) {
+    const int j = static_cast<int>(w / nk), k = static_cast<int>(w % nk);
+    const int entry = P.list[j];
+    if (((entry & 1) ? wide_tries : 0) + lane >= P.opt.line_search_max_iterations) continue;
+    const PLane<M, W, 1> L(P, s_blob, entry >> 1, lane, 0, true);
+    const double* zc = P.CAND + static_cast<size_t>(w) * nz * kWarp + lane;
+    double x[n], u[m];
+    ALTRO_UNROLL
+    for (int q = 0; q < n; ++q) x[q] = zc[q * kWarp];
+    ALTRO_UNROLL
+    for (int q = 0; q < m; ++q) u[q] = zc[(n + q) * kWarp];
+    const AlPen pen(L.sc(S_PENALTY));
+    const double* lam = P.pmax > 0 ? L.lam(k) : nullptr;
+    P.COSTK[static_cast<size_t>(w) * kWarp + lane] = knot_cost<n, m, W>(L.D, k, x, u, lam, pen, nullptr);
+  }
+}
+
+template <class M, int W>
+__global__ void __launch_bounds__(kLsWarps* kWarp) k_acc_deep(SolverParams P, int mode, int wide_tries) {
+  extern __shared__ __align__(128) char smem[];  // per warp: N doubles for the winner's gains
+  const int count = P.counters[3];
+  const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
+  const int j = blockIdx.x * kLsWarps + warp;
+  if (j >= count) return;
+  using LaneT = PLane<M, W, 1>;
+  constexpr int nz = LaneT::nz, GZ = kWarp / W, n = M::n, m = M::m;
+  const int N = P.N;
+  double* gbuf = reinterpret_cast<double*>(smem) + static_cast<size_t>(warp) * N;
+  const int entry = P.list[j];
+  const LaneT L(P, nullptr, entry >> 1, lane, 0, true);
+  const int done0 = (entry & 1) ? wide_tries : 0;
+  const int t = done0 + lane;
+  const bool mine = t < P.opt.line_search_max_iterations;
+  const int zsel = L.is(I_ZSEL);
+  int st = L.is(I_STATUS), st_try = st;
+  const double J0 = L.sc(S_J0), dV0 = L.sc(S_DV0), dV1 = L.sc(S_DV1);
+  double csrc = L.sc(S_CSRC_ALPHA);
+  double J = 0.0;
+  if (mine) {
+    st_try = P.TRYST[j * kWarp + lane];
+    const double* ck = P.COSTK + static_cast<size_t>(j) * (N + 1) * kWarp + lane;
+    for (int k = 0; k <= N; ++k) J += ck[k * kWarp];
+  }
+  PLsResult r = p_accept<1>(P.opt, 0, lane, true, mine, mine && st_try == kUnsolved, J, try_alpha(P.opt, t), st_try,
+                            J0, dV0, dV1, done0, st, csrc);
+  r.exhausted = true;  // one round covers every remaining try (the host guarantees max <= wide + 32)
+  const double* cand = P.CAND + static_cast<size_t>(j) * (N + 1) * nz * kWarp;
+  const int new_zsel = (zsel + 1) % (GZ + 1);
+  if (r.success) {
+    for (int k = lane; k < N; k += kWarp)
+      gbuf[k] = knot_gain<m>(L.kd(k) + m * n * W, W, cand + (static_cast<size_t>(k) * nz + n) * kWarp + r.slot, kWarp);
+    const double* src = cand + r.slot;
+    double* dst = L.z(new_zsel, 0);
+    const int total = (N + 1) * nz;
+    for (int e = lane; e < total; e += kWarp) dst[static_cast<size_t>(e) * W] = src[static_cast<size_t>(e) * kWarp];
+    __syncwarp();
+    if (lane == 0) {
+      double gs = 0.0;
+      for (int k = 0; k < N; ++k) gs += gbuf[k];
+      r.gsum = gs;
+    }
+  }
+  if (lane == 0) p_finish(L, mode, r, new_zsel, zsel, J0, csrc, st);
 }
 
 // First G = 32/W tries of every instance in kPhInner whose previous search did not fail
@@ -473,6 +892,31 @@ __global__ void k_microbench(SolverParams P, double* sink, long long* out, int r
       for (int q = 0; q < n * n; ++q) Pm[q] = 0.5 * Pm[q] + 5.0 * lxx[q]; }
     acc += Pm[0] + p[0] + dV0 + dV1; }
   t1 = clock64(); if (lane == 0) out[o] = (t1 - t0) / reps; ++o;
+  // whole closed-loop rollouts of instance 0 (one instance per warp mapping), cycles per knot
+  {
+    __shared__ double stg_s[2 * 160];
+    const PLane<M, W, 1> L(P, smem, 0, lane, 0, true);
+    double* cand = P.CAND + lane;
+    const int nzz = n + m;
+    double J, g;
+    int st = kUnsolved;
+#define ALTRO_PROBE(mask)                                                                              \
+    t0 = clock64();                                                                                  \
+    p_rollout<M, W, 1, mask>(L, stg_s, true, 0, cand, kWarp, nzz * kWarp, 0.5, 10.0, J, g, st);      \
+    t1 = clock64();                                                                                  \
+    acc += J + g;                                                                                    \
+    if (lane == 0) out[o] = (t1 - t0) / (P.N + 1);                                                   \
+    ++o;
+    ALTRO_PROBE(0)
+    ALTRO_PROBE(0)
+    ALTRO_PROBE(1)
+    ALTRO_PROBE(2)
+    ALTRO_PROBE(4)
+    ALTRO_PROBE(8)
+    ALTRO_PROBE(16)
+    ALTRO_PROBE(31)
+#undef ALTRO_PROBE
+  }
   sink[lane] = acc;
 }
 

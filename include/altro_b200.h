@@ -256,7 +256,7 @@ int altro_b200_get_scalars_host(altro_b200_solver* s, double* reg, double* dV0, 
 size_t altro_b200_backward_pass_bytes(const altro_b200_solver* s);
 /* number of kernels this library has launched on behalf of `s` since creation */
 int64_t altro_b200_kernel_launches(const altro_b200_solver* s);
-/* latency probe: cycles per call of the per-knot device functions on one warp (cycles[16]) */
+/* latency probe: cycles per call of the per-knot device functions on one warp (cycles[32]) */
 int altro_b200_microbench(altro_b200_solver* s, long long* cycles, int reps);
 /* device bytes held by the solver */
 size_t altro_b200_device_bytes(const altro_b200_solver* s);

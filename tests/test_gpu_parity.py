@@ -19,13 +19,18 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-@pytest.fixture(scope="module")
-def gpu():
+@pytest.fixture(scope="module", params=["phased", "fused"])
+def gpu(request):
+    """The package with the default engine set: every test of this module runs once per engine
+    (phased: throughput kernels per phase, the default; fused: one persistent kernel)."""
     import torch
     if not torch.cuda.is_available():
         pytest.fail("GPU tests need a CUDA device (the product path has no CPU fallback)")
     import altro_cpp_b200 as pkg
-    return pkg
+    pkg.set_default_engine(request.param)
+    pkg._test_engine = request.param
+    yield pkg
+    pkg.set_default_engine(None)
 
 
 def rel_err(a, b):
@@ -563,3 +568,79 @@ def test_constraint_values_match_definitions_and_max_violation(gpu):
     s2 = gpu.BatchSolver(spec, 4, use_constraints=False)
     s2.set_inputs(X0[:4])
     assert s2.constraint_values(5).shape == (4, 0)
+
+
+# ------------------------------------------------------------------------------------------
+# engines and options that must not change results
+# ------------------------------------------------------------------------------------------
+def _solve(gpu, spec, X0, engine, options=None, env=None):
+    import os
+    gpu.set_default_engine(engine)
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        s = gpu.BatchSolver(spec, X0.shape[0], options=options)
+        assert s.engine == engine
+        s.set_inputs(X0)
+        s.solve_al()
+        r = s.results()
+        X, U = s.trajectory()
+        K, d = s.gains()
+    finally:
+        gpu.set_default_engine(gpu._test_engine)
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return r, X, U, K, d
+
+
+def _same(a, b):
+    ra, Xa, Ua, Ka, da = a
+    rb, Xb, Ub, Kb, db = b
+    return (np.array_equal(Xa, Xb) and np.array_equal(Ua, Ub) and np.array_equal(Ka, Kb) and np.array_equal(da, db)
+            and all(np.array_equal(ra[k], rb[k]) for k in ("cost", "viol", "status", "iters")))
+
+
+@pytest.mark.parametrize("case", ["c2", "c3", "c4"])
+def test_engines_are_bit_identical(gpu, case):
+    """Phased engine (fused and split line-search kernels) == fused engine, bit for bit: status,
+    iteration counts, cost, violation, trajectories and gains of every instance."""
+    if case == "c2":
+        spec, scale, B = P.unicycle_problem(P.K_THREE_OBSTACLES), P.UNICYCLE_X0_SCALE, 300
+    elif case == "c3":
+        spec, scale, B = P.triple_integrator_problem(dof=2, N=50, add_constraints=True), P.TRIPLE_INTEGRATOR_X0_SCALE, 130
+    else:
+        spec, scale, B = P.cartpole_problem(N=200), P.CARTPOLE_X0_SCALE, 40
+    X0 = P.perturbed_initial_states(spec, B, scale)
+    fused = _solve(gpu, spec, X0, "fused")
+    for env in ({"ALTRO_B200_SPLIT_MAX": "0"}, {"ALTRO_B200_SPLIT_MAX": "1000000"},
+                {"ALTRO_B200_SPLIT_MAX": "64", "ALTRO_B200_OVERLAP": "0"}, {"ALTRO_B200_REPACK_PCT": "0"}):
+        assert _same(_solve(gpu, spec, X0, "phased", env=env), fused), env
+
+
+@pytest.mark.parametrize("engine", ["phased", "fused"])
+def test_skip_repeated_iterations_keeps_results(gpu, engine):
+    """The opt-in stall skip accounts for provably repeated inner iterations without running them:
+    every output, including the iteration counters and the kMaxInnerIterations statuses, is
+    bit-identical to the faithful run."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    X0 = P.perturbed_initial_states(spec, 200, P.UNICYCLE_X0_SCALE)
+    faithful = _solve(gpu, spec, X0, engine)
+    o = gpu.default_options()
+    o.skip_repeated_iterations = 1
+    skipped = _solve(gpu, spec, X0, engine, options=o)
+    assert (faithful[0]["status"] == 7).any(), "the sample should contain instances that stall"
+    assert _same(skipped, faithful)
+
+
+def test_long_line_search_uses_looping_kernels(gpu, oracle):
+    """line_search_max_iterations beyond one wide + one deep round (4 + 32 tries)."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    X0 = P.perturbed_initial_states(spec, 24, P.UNICYCLE_X0_SCALE)
+    o = gpu.default_options()
+    o.line_search_max_iterations = 40
+    o.max_iterations_inner = 30
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, options=o, max_mismatch_frac=0.0)
+    assert errs["X"] <= 1e-8
