@@ -175,6 +175,10 @@ class BatchSolver:
         self._call("solver_set_inputs_dev", ctypes.cast(x0_ptr, _dp), ctypes.cast(U0_ptr, _dp), _p(unom),
                    _stream_ptr(stream))
 
+    def trajectory_dev(self, X_ptr: int, U_ptr: int, stream=None):
+        """Current trajectories into device buffers X [B][N+1][n], U [B][N][m] (raw device pointers)."""
+        self._call("get_trajectory_dev", ctypes.cast(X_ptr, _dp), ctypes.cast(U_ptr, _dp), _stream_ptr(stream))
+
     def set_states(self, X, stream=None):
         X = _f64(np.broadcast_to(_f64(X), (self.B, self.N + 1, self.n)))
         self._call("solver_set_states_host", _p(X), _stream_ptr(stream))

@@ -664,9 +664,13 @@ __device__ __forceinline__ void finish_inner(const DevOptions& o, int N, int mod
 // ------------------------------------------------------------------------------------------
 constexpr int kSolveWarps = ALTRO_SOLVE_WARPS;
 
-template <class M, int W>
-__global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB_NARROW : ALTRO_SOLVE_MINB)) k_solve(SolverParams P, int mode,
-                                                                               int budget, int parts) {
+// kParts: compile-time mask on `parts` (1 outer step + solve start, 2 inner iteration, 4 overlapped
+// mode).  The phased engine instantiates kParts = 5: the inner iteration is compiled out, which
+// leaves a small kernel without register spills for the outer steps.
+template <class M, int W, int kParts = 7>
+__global__ void __launch_bounds__(kSolveWarps* kWarp, ((W <= 4 || (kParts & 2) == 0) ? ALTRO_SOLVE_MINB_NARROW : ALTRO_SOLVE_MINB)) k_solve(SolverParams P, int mode,
+                                                                               int budget, int parts_rt) {
+  const int parts = parts_rt & kParts;
   extern __shared__ __align__(128) char smem[];
   copy_blob(P.blob, smem, P.blob_bytes);
   const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -715,7 +719,8 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
   const bool was_reported = phase >= kPhReported;
   // overlapped mode of the phased engine (parts & 4): instances in kPhInner belong to the
   // inner-iteration kernels running concurrently on another stream — hands off their state
-  const bool foreign = (parts & 4) && phase == kPhInner;
+  // (a pending phase seen here was written during this slot by those kernels: still theirs)
+  const bool foreign = (parts & 4) && (phase == kPhInner || phase < 0);
   if (phase == kPhAlInit) {  // AugmentedLagrangianiLQR::Init, al_solver.hpp:287-302 (Q10)
     if (o.reset_duals && has_con && L.a == 0) {
       for (int k = 0; k <= N; ++k) {
