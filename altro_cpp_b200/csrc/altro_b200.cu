@@ -1011,7 +1011,8 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
 // count and, when enough instances are done, re-packs the rest densely.
 static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
   DeviceGuard guard(s->device);
-  const int poll = std::max(1, env_int("ALTRO_B200_POLL", 4));
+  const int outer_period = std::max(1, env_int("ALTRO_B200_OUTER_PERIOD", 4));
+  const int poll = outer_period * std::max(1, env_int("ALTRO_B200_POLL", 4) / outer_period);
   const int repack_pct = env_int("ALTRO_B200_REPACK_PCT", 70);  // 0 disables re-packing
   int rc;
   if ((rc = s->ensure_phased())) return rc;
@@ -1065,7 +1066,10 @@ static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
       PH(cur_ops.solve(*cur, mode, 1, 1 | 4, s->st2), "k_solve");
       if (polling) CU(cudaMemcpyAsync(s->h_count, cur->counters, sizeof(int), cudaMemcpyDeviceToHost, s->st2));
       CU(cudaEventRecord(s->ev_join, s->st2));
-    } else {
+    } else if (slot % outer_period == 0) {
+      // outer steps are serial chains over the horizon whatever the number of instances taking one:
+      // they are batched every outer_period slots (an instance that ended an iLQR solve waits for
+      // the next batch; results do not depend on when it is served)
       PH(cur_ops.solve(*cur, mode, 1, 1, st), "k_solve");
       if (polling) CU(cudaMemcpyAsync(s->h_count, cur->counters, sizeof(int), cudaMemcpyDeviceToHost, st));
     }

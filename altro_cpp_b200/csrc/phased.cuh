@@ -773,8 +773,11 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_ls_wide(SolverParams P, int
 // entry = (instance << 1) | from_wide: from_wide = 1 -> the first `wide_tries` tries are done.
 // Candidates go to the warp's scratch block of P.CAND; the accepted one is copied into the
 // instance's next trajectory buffer by the whole warp.
+#ifndef ALTRO_DEEP_MINB
+#define ALTRO_DEEP_MINB 4
+#endif
 template <class M, int W>
-__global__ void __launch_bounds__(kLsWarps* kWarp) k_ls_deep(SolverParams P, int mode, int wide_tries) {
+__global__ void __launch_bounds__(kLsWarps* kWarp, ALTRO_DEEP_MINB) k_ls_deep(SolverParams P, int mode, int wide_tries) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.counters[3];
   if (static_cast<int>(blockIdx.x) * kLsWarps >= count) return;

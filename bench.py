@@ -268,6 +268,7 @@ def main():
         launches = solver.kernel_launches() - l0
         ms = e0.elapsed_time(e1) / args.steps
     res = solver.results()
+    X_sol, U_sol = solver.trajectory()  # kept for the bit-identity check of the secondary measurement
 
     # ---- e2e: host buffers through altro_b200_solve_al_host (pinned memory)
     pin_x0 = torch.from_numpy(X0_host).pin_memory()
@@ -339,7 +340,7 @@ def main():
             ms_skip = e6.elapsed_time(e7) / args.steps
         res2 = solver2.results()
         X2, U2 = solver2.trajectory()
-        X1, U1 = solver.trajectory()
+        X1, U1 = X_sol, U_sol
         identical = bool(np.array_equal(res2["cost"], res["cost"]) and np.array_equal(res2["iters"], res["iters"])
                          and np.array_equal(res2["status"], res["status"]) and np.array_equal(X1, X2)
                          and np.array_equal(U1, U2))

@@ -13,14 +13,20 @@ X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
 s = pkg.BatchSolver(spec, B)
 hs = []
 prev = None
-for rep in range(3):
+for rep in range(int(os.environ.get('REPS', '3'))):
     s.set_inputs(X0); s.solve_al()
     r = s.results(); X, U = s.trajectory()
     hs.append(hashlib.sha1(r["cost"].tobytes() + r["iters"].tobytes() + X.tobytes() + U.tobytes()).hexdigest()[:10])
     if prev is not None:
-        bad = np.where(np.any(prev[0] != r["iters"], axis=1) | (prev[1] != r["cost"]))[0]
-        if len(bad): print("   differing instances:", len(bad), bad[:8].tolist(), prev[0][bad[:4]].tolist(), r["iters"][bad[:4]].tolist())
-    prev = (r["iters"].copy(), r["cost"].copy())
+        dX = np.abs(prev[2] - X).reshape(B, -1).max(axis=1); dU = np.abs(prev[3] - U).reshape(B, -1).max(axis=1)
+        bad = np.where(np.any(prev[0] != r["iters"], axis=1) | (prev[1] != r["cost"]) | (dX > 0) | (dU > 0) | (prev[4] != r["viol"]))[0]
+        if len(bad):
+            print("   differing instances:", len(bad), bad[:16].tolist())
+            print("     iters", prev[0][bad[:8]].tolist(), r["iters"][bad[:8]].tolist())
+            print("     dcost", (prev[1][bad[:8]] - r["cost"][bad[:8]]).tolist())
+            print("     dX", dX[bad[:8]].tolist(), "dU", dU[bad[:8]].tolist(), "dviol", (prev[4][bad[:8]] - r["viol"][bad[:8]]).tolist())
+            b0 = bad[0]; kx = np.where(np.abs(prev[2][b0] - X[b0]).max(axis=1) > 0)[0]; print("     knots with dX != 0 for", b0, ":", kx[:10].tolist(), "...", len(kx))
+    prev = (r["iters"].copy(), r["cost"].copy(), X.copy(), U.copy(), r["viol"].copy())
 print(s.engine, hs)
 ''' % ROOT
 configs = [{"ALTRO_B200_SPLIT_MAX": "0", "ALTRO_B200_OVERLAP": "0"},
