@@ -615,8 +615,11 @@ def test_engines_are_bit_identical(gpu, case):
         spec, scale, B = P.cartpole_problem(N=200), P.CARTPOLE_X0_SCALE, 40
     X0 = P.perturbed_initial_states(spec, B, scale)
     fused = _solve(gpu, spec, X0, "fused")
+    # scheduling knobs of the phased engine: which line-search kernels run, how often outer steps
+    # are batched, how often the host polls, whether unfinished instances are re-packed
     for env in ({"ALTRO_B200_SPLIT_MAX": "0"}, {"ALTRO_B200_SPLIT_MAX": "1000000"},
-                {"ALTRO_B200_SPLIT_MAX": "64", "ALTRO_B200_OVERLAP": "0"}, {"ALTRO_B200_REPACK_PCT": "0"}):
+                {"ALTRO_B200_SPLIT_MAX": "64", "ALTRO_B200_OUTER_PERIOD": "1"}, {"ALTRO_B200_REPACK_PCT": "0"},
+                {"ALTRO_B200_OUTER_PERIOD": "3", "ALTRO_B200_REPACK_PCT": "95"}, {"ALTRO_B200_OUTER_PERIOD": "8"}):
         assert _same(_solve(gpu, spec, X0, "phased", env=env), fused), env
 
 
