@@ -19,6 +19,7 @@ HEADERS = ["common.cuh", "device.cuh", "kernels.cuh", "large.cuh", os.path.join(
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
+    "-split-compile", "0",  # the kernels are independent: let nvcc optimise / assemble them in parallel
     "-Xcompiler", "-fPIC", "-shared",
     "-cudart", "shared",
 ]
