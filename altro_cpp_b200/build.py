@@ -14,7 +14,13 @@ LIB = os.path.join(HERE, "libaltro_b200.so")
 SOURCES = ["altro_b200.cu", "altro_b200_large.cu"]
 # per-source extra flags: the large-state path is compiled without FMA contraction (bit parity)
 EXTRA = {"altro_b200_large.cu": ["-fmad=false"]}
-HEADERS = ["common.cuh", "device.cuh", "kernels.cuh", "large.cuh", os.path.join("..", "..", "include", "altro_b200.h")]
+
+
+def _headers():
+    """Every header a source can include: all of csrc/ plus the public C ABI (globbed, so a new header cannot be missed)."""
+    hs = [f for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", ".hpp"))]
+    return hs + [os.path.join("..", "..", "include", "altro_b200.h")]
+
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -29,7 +35,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    for f in SOURCES + HEADERS:
+    for f in SOURCES + _headers():
         p = os.path.join(CSRC, f)
         if os.path.exists(p) and os.path.getmtime(p) > t:
             return True
@@ -64,5 +70,16 @@ def build(force: bool = False, verbose: bool = False, out: str = LIB, defines=()
     return out
 
 
+DEV_LIB = os.path.join(HERE, "libaltro_b200_dev.so")
+
+
+def build_dev(verbose: bool = False) -> str:
+    """Kernel-tuning build: unicycle, tile width 8 only (ALTRO_DEV_BUILD).  Use with ALTRO_B200_LIB=<path>."""
+    return build(force=True, verbose=verbose, out=DEV_LIB, defines=("ALTRO_DEV_BUILD",))
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--dev" in sys.argv:
+        print(build_dev(verbose="-v" in sys.argv))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -227,6 +227,7 @@ class BatchSolver:
     def update_expansions(self, stream=None): self._call("update_expansions", _stream_ptr(stream))
     def backward_pass(self, stream=None): self._call("backward_pass", _stream_ptr(stream))
     def backward_pass_stream_only(self, stream=None): self._call("backward_pass_stream_only", _stream_ptr(stream))
+    def backward_pass_insolve(self, stream=None): self._call("backward_pass_insolve", _stream_ptr(stream))
     def backward_pass_fused(self, stream=None): self._call("backward_pass_fused", _stream_ptr(stream))
     def forward_pass(self, stream=None): self._call("forward_pass", _stream_ptr(stream))
     def update_convergence_statistics(self, stream=None):

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "outer.cuh"
 #include "phased.cuh"
 
 // large-state path, compiled in its own translation unit (altro_b200_large.cu) without FMA
@@ -119,7 +120,7 @@ int build_blob(const altro_b200_problem& p, bool use_constraints, std::vector<ch
     }
     conset_id[k] = id;
   }
-  const int cost_stride = n * n + m * m + n * m + n + m + 1;
+  const int cost_stride = n * n + m * m + n * m + n + m + 1 + 1;  // + the CostShape slot
   auto align = [](size_t v, size_t a) { return (v + a - 1) / a * a; };
   BlobHeader h;
   std::memset(&h, 0, sizeof(h));
@@ -154,9 +155,22 @@ int build_blob(const altro_b200_problem& p, bool use_constraints, std::vector<ch
   std::memcpy(b + h.off_t, p.t.data(), sizeof(float) * (N + 1));
   if (!p.params.empty())
     std::memcpy(b + h.off_params, p.params.data(), sizeof(double) * p.params.size());
-  for (size_t i = 0; i < p.costs.size(); ++i)
-    std::memcpy(b + h.off_cost + sizeof(double) * cost_stride * i, p.costs[i].data.data(),
-                sizeof(double) * cost_stride);
+  for (size_t i = 0; i < p.costs.size(); ++i) {
+    const std::vector<double>& c = p.costs[i].data;  // Q, R, H, q, r, c
+    double* dst = reinterpret_cast<double*>(b + h.off_cost + sizeof(double) * cost_stride * i);
+    std::memcpy(dst, c.data(), sizeof(double) * (cost_stride - 1));
+    bool diag = true;
+    for (int col = 0; col < n; ++col)
+      for (int row = 0; row < n; ++row)
+        if (row != col && c[row + col * n] != 0.0) diag = false;
+    for (int col = 0; col < m; ++col)
+      for (int row = 0; row < m; ++row)
+        if (row != col && c[n * n + row + col * m] != 0.0) diag = false;
+    for (int q = 0; q < n * m; ++q)
+      if (c[n * n + m * m + q] != 0.0) diag = false;
+    if (std::getenv("ALTRO_B200_DENSE_COST")) diag = false;  // test knob: the dense path gives the same bits
+    dst[cost_stride - 1] = diag ? kCostDiagonal : kCostDense;
+  }
   std::memcpy(b + h.off_conset, sets.data(), sizeof(ConSet) * sets.size());
   *pmax_out = pmax;
   return 0;
@@ -176,6 +190,8 @@ struct Ops {
   cudaError_t (*backward_phased)(const SolverParams&, cudaStream_t) = nullptr;
   cudaError_t (*ls_wide)(const SolverParams&, int mode, cudaStream_t) = nullptr;
   cudaError_t (*ls_deep)(const SolverParams&, int mode, int max_instances, cudaStream_t) = nullptr;
+  // outer-loop work of the phased engine on a dense list (outer.cuh); returns the kernels launched
+  cudaError_t (*outer_step)(const SolverParams&, int mode, int sm_count, cudaStream_t, int* nlaunch) = nullptr;
   cudaError_t (*microbench)(const SolverParams&, double* sink, long long* out, int reps, cudaStream_t) = nullptr;
   // split line search: rollout / per-knot cost / acceptance kernels (wide: all tiles; deep: the list)
   cudaError_t (*ls_split_wide)(const SolverParams&, int mode, cudaStream_t) = nullptr;
@@ -199,14 +215,6 @@ Ops make_ops() {
     const int smem = solve_smem<M, W>(P);
     cudaError_t e = cudaFuncSetAttribute(k_solve<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    if constexpr (W == kPhasedTile) {
-      if ((parts & 2) == 0) {  // outer steps of the phased engine: the kernel without the inner iteration
-        e = cudaFuncSetAttribute(k_solve<M, W, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        k_solve<M, W, 5><<<(P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st>>>(P, mode, budget, parts);
-        return cudaGetLastError();
-      }
-    }
     k_solve<M, W><<<(P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st>>>(P, mode, budget, parts);
     return cudaGetLastError();
   };
@@ -299,11 +307,36 @@ Ops make_ops() {
       k_ls_wide<M, W><<<(P.T + kLsWarps - 1) / kLsWarps, kLsWarps * kWarp, smem, st>>>(P, mode);
       return cudaGetLastError();
     };
+    o.outer_step = [](const SolverParams& P, int mode, int sm_count, cudaStream_t st, int* nlaunch) -> cudaError_t {
+      // grids: enough CTAs for every instance to have outer work pending (first slot of a solve),
+      // capped at a few waves; the kernels loop over the device-side list with a grid stride
+      const int nk = P.N + 1;
+      const int lane_grid = std::min((P.B + kOuterThreads - 1) / kOuterThreads, sm_count * 8);
+      const long items = static_cast<long>(P.B) * nk;
+      const int item_grid = static_cast<int>(std::min<long>((items + kOuterThreads - 1) / kOuterThreads, sm_count * 16));
+      k_outer_select<<<(P.B + 255) / 256, 256, 0, st>>>(P);
+      k_outer_rollout<M, W, true><<<lane_grid, kOuterThreads, 0, st>>>(P);
+      k_outer_duals<M, W><<<item_grid, kOuterThreads, 0, st>>>(P);
+      k_outer_decide<<<lane_grid, kOuterThreads, 0, st>>>(P);
+      k_outer_rollout<M, W, false><<<lane_grid, kOuterThreads, 0, st>>>(P);
+      k_outer_cost<M, W><<<item_grid, kOuterThreads, 0, st>>>(P);
+      k_outer_finish<<<lane_grid, kOuterThreads, 0, st>>>(P, mode);
+      *nlaunch = 7;
+      return cudaGetLastError();
+    };
     o.ls_deep = [](const SolverParams& P, int mode, int max_instances, cudaStream_t st) -> cudaError_t {
-      const int smem = ((P.blob_bytes + 15) / 16) * 16 + kLsWarps * p_stage_doubles<M>(P.pmax, 1) * sizeof(double);
-      cudaError_t e = cudaFuncSetAttribute(k_ls_deep<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      k_ls_deep<M, W><<<(max_instances + kLsWarps - 1) / kLsWarps, kLsWarps * kWarp, smem, st>>>(P, mode, kWarp / W);
+      const int blob = ((P.blob_bytes + 15) / 16) * 16;
+      if (P.opt.line_search_max_iterations - kWarp / W <= kWarp / 2) {  // two instances per warp
+        const int smem = blob + kLsWarps * p_deep_warp_doubles<M>(P.pmax, P.N, 2) * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(k_ls_deep<M, W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        k_ls_deep<M, W, 2><<<(max_instances + 2 * kLsWarps - 1) / (2 * kLsWarps), kLsWarps * kWarp, smem, st>>>(P, mode, kWarp / W);
+      } else {
+        const int smem = blob + kLsWarps * p_deep_warp_doubles<M>(P.pmax, P.N, 1) * sizeof(double);
+        cudaError_t e = cudaFuncSetAttribute(k_ls_deep<M, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        k_ls_deep<M, W, 1><<<(max_instances + kLsWarps - 1) / kLsWarps, kLsWarps * kWarp, smem, st>>>(P, mode, kWarp / W);
+      }
       return cudaGetLastError();
     };
   }
@@ -323,22 +356,40 @@ Ops make_large_ops_32_8() {
   return o;
 }
 
+// Tile widths with instantiations.  ALTRO_DEV_BUILD (altro_cpp_b200/build.py --dev): the unicycle at
+// the phased engine's tile width only — a kernel-tuning build that compiles in well under a minute.
+#ifdef ALTRO_DEV_BUILD
+constexpr int kWidths[] = {8};
+#else
+constexpr int kWidths[] = {2, 4, 8, 16, 32};
+#endif
+bool width_available(int W) {
+  for (int w : kWidths)
+    if (w == W) return true;
+  return false;
+}
+
 template <class M>
 bool ops_for_width(int W, Ops* out) {
+  if (!width_available(W)) return false;
+#ifndef ALTRO_DEV_BUILD
   if (W == 2) { if (out) *out = make_ops<M, 2>(); return true; }
   if (W == 4) { if (out) *out = make_ops<M, 4>(); return true; }
-  if (W == 8) { if (out) *out = make_ops<M, 8>(); return true; }
   if (W == 16) { if (out) *out = make_ops<M, 16>(); return true; }
   if (W == 32) { if (out) *out = make_ops<M, 32>(); return true; }
+#endif
+  if (W == 8) { if (out) *out = make_ops<M, 8>(); return true; }
   return false;
 }
 
 bool lookup_ops(int n, int m, int model, int W, Ops* out) {
   if (model == kUnicycle && n == 3 && m == 2) return ops_for_width<Unicycle>(W, out);
+#ifndef ALTRO_DEV_BUILD
   if (model == kTripleIntegrator && n == 6 && m == 2) return ops_for_width<TripleIntegrator<2>>(W, out);
   if (model == kTripleIntegrator && n == 3 && m == 1) return ops_for_width<TripleIntegrator<1>>(W, out);
   if (model == kCartpole && n == 4 && m == 1) return ops_for_width<Cartpole>(W, out);
   if (model == kLinear && n == 32 && m == 8) { if (out) *out = make_large_ops_32_8(); return true; }
+#endif
   return false;
 }
 
@@ -367,10 +418,11 @@ int default_engine() {
 int choose_tile_width(int batch, int sm_count) {
   if (const char* e = std::getenv("ALTRO_B200_TILE")) {
     const int w = std::atoi(e);
-    if (w == 2 || w == 4 || w == 8 || w == 16 || w == 32) return w;
+    if (width_available(w)) return w;
   }
-  int pick = 32;
+  int pick = kWidths[sizeof(kWidths) / sizeof(int) - 1];
   for (int w = 32; w >= 2; w /= 2) {
+    if (!width_available(w)) continue;
     const long warps = (batch + w - 1) / w;
     if (warps <= static_cast<long>(sm_count) * resident_warps_per_sm(w)) pick = w;
   }
@@ -382,6 +434,11 @@ int choose_tile_width(int batch, int sm_count) {
 // ------------------------------------------------------------------------------------------
 // Solver
 // ------------------------------------------------------------------------------------------
+static int env_split_max() {
+  const char* e = std::getenv("ALTRO_B200_SPLIT_MAX");
+  return e ? std::atoi(e) : 2048;
+}
+
 struct altro_b200_solver {
   int n, m, N, B, T, Bp, W, G, pmax, device, use_al;
   int engine = ALTRO_B200_ENGINE_FUSED;
@@ -395,6 +452,8 @@ struct altro_b200_solver {
   int64_t launches = 0;
   std::vector<void*> allocs;
   bool inputs_set = false;
+  bool insolve_ready = false;     // measurement: phases set up for altro_b200_backward_pass_insolve
+  bool expansions_valid = false;  // EXP holds the records altro_b200_update_expansions wrote for the current Z_
   int model = 0, sm_count = 148;
   std::vector<int> p_knot;  // constraint rows per knot (ALCost order)
   // secondary workspaces: unfinished instances are re-packed into them between k_solve launches
@@ -406,14 +465,28 @@ struct altro_b200_solver {
   } sec[2];
   int* d_list = nullptr;
   int* h_count = nullptr;  // pinned
-  cudaStream_t st2 = nullptr;            // phased engine, overlapped mode: outer-step kernels
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   int alloc(void** p, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes);
     if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     allocs.push_back(*p);
     dev_bytes += bytes;
+    // debug aid (tools/gpu_repro.py): fill every allocation with 0xFF (NaN doubles, -1 ints) so that a
+    // read of memory the solve never wrote shows up in the results instead of depending on the heap
+    if (std::getenv("ALTRO_B200_POISON")) {
+      cudaMemset(*p, 0xFF, bytes);
+      cudaDeviceSynchronize();
+    }
+    return 0;
+  }
+  // Lazily allocated arrays that must start as zeros.  cudaMemset runs on the legacy default stream,
+  // which a non-blocking user stream (e.g. a torch stream) does not wait for: synchronise so that the
+  // zeros cannot land after kernels queued next on the caller's stream.
+  int alloc_zeroed(void** p, size_t bytes) {
+    int rc = alloc(p, bytes);
+    if (rc) return rc;
+    cudaMemset(*p, 0, bytes);
+    cudaDeviceSynchronize();
     return 0;
   }
   int ensure_io(size_t bytes) {
@@ -423,38 +496,37 @@ struct altro_b200_solver {
     if (e != cudaSuccess) { d_io = nullptr; io_bytes = 0; return fail(ALTRO_B200_ERR_CUDA, "cudaMalloc(staging) failed"); }
     io_bytes = bytes;
     dev_bytes += bytes;
+    if (std::getenv("ALTRO_B200_POISON")) cudaMemset(d_io, 0xFF, bytes);
     return 0;
   }
-  int ensure_phased() {  // scratch of the phased engine: expansions, deep line-search candidates, list
+  int ensure_phased() {  // scratch of the phased engine: expansions, lists, line-search / outer-step scratch
     const size_t knots = static_cast<size_t>(T) * (N + 1) * W * sizeof(double);
     int rc;
-    if (!P.EXP) {
-      if ((rc = alloc(reinterpret_cast<void**>(&P.EXP), knots * exp_fields(n, m)))) return rc;
-      cudaMemset(P.EXP, 0, knots * exp_fields(n, m));
-    }
+    if (!P.EXP && (rc = alloc_zeroed(reinterpret_cast<void**>(&P.EXP), knots * exp_fields(n, m)))) return rc;
+    // the split line-search kernels only run while at most split_cap instances are in flight
+    P.split_cap = std::min(Bp, std::max(kWarp, env_split_max()));
     if (!P.CAND) {
-      const size_t bytes = static_cast<size_t>(Bp) * (N + 1) * (n + m) * kWarp * sizeof(double);
+      const size_t bytes = static_cast<size_t>(P.split_cap) * (N + 1) * (n + m) * kWarp * sizeof(double);
       if ((rc = alloc(reinterpret_cast<void**>(&P.CAND), bytes))) return rc;
     }
     if (!P.list && (rc = alloc(reinterpret_cast<void**>(&P.list), static_cast<size_t>(Bp) * sizeof(int)))) return rc;
+    if (!P.olist && (rc = alloc(reinterpret_cast<void**>(&P.olist), static_cast<size_t>(Bp) * sizeof(int)))) return rc;
     if (!P.COSTK) {
-      if ((rc = alloc(reinterpret_cast<void**>(&P.COSTK), static_cast<size_t>(N + 1) * Bp * kWarp * sizeof(double)))) return rc;
-      if ((rc = alloc(reinterpret_cast<void**>(&P.TRYST), static_cast<size_t>(Bp) * kWarp * sizeof(int)))) return rc;
+      // rows of 32 per-knot costs: one per tile (wide kernels) or per list entry (split deep kernels);
+      // the outer-step kernels use it as [entry][N+1], at most Bp entries
+      const size_t rows = std::max<size_t>(std::max(T, P.split_cap), (static_cast<size_t>(Bp) + kWarp - 1) / kWarp);
+      if ((rc = alloc(reinterpret_cast<void**>(&P.COSTK), static_cast<size_t>(N + 1) * rows * kWarp * sizeof(double)))) return rc;
+      if ((rc = alloc(reinterpret_cast<void**>(&P.TRYST), rows * kWarp * sizeof(int)))) return rc;
     }
     return 0;
   }
   int ensure_stepwise() {  // EXP / CTG / COSTS are only needed by the step-wise API
     const size_t knots = static_cast<size_t>(T) * (N + 1) * W * sizeof(double);
     int rc;
-    if (!P.EXP) {
-      if ((rc = alloc(reinterpret_cast<void**>(&P.EXP), knots * exp_fields(n, m)))) return rc;
-      cudaMemset(P.EXP, 0, knots * exp_fields(n, m));
-    }
+    if (!P.EXP && (rc = alloc_zeroed(reinterpret_cast<void**>(&P.EXP), knots * exp_fields(n, m)))) return rc;
     if (!P.CTG) {
-      if ((rc = alloc(reinterpret_cast<void**>(&P.CTG), knots * (n * n + n)))) return rc;
-      if ((rc = alloc(reinterpret_cast<void**>(&P.COSTS), knots))) return rc;
-      cudaMemset(P.CTG, 0, knots * (n * n + n));
-      cudaMemset(P.COSTS, 0, knots);
+      if ((rc = alloc_zeroed(reinterpret_cast<void**>(&P.CTG), knots * (n * n + n)))) return rc;
+      if ((rc = alloc_zeroed(reinterpret_cast<void**>(&P.COSTS), knots))) return rc;
     }
     return 0;
   }
@@ -593,7 +665,7 @@ void altro_b200_default_options(altro_b200_options* o) {  // solver_options.hpp:
   o->penalty_scaling = 10.0;
 }
 
-int altro_b200_is_supported(int n, int m, int model) { return lookup_ops(n, m, model, 32, nullptr) ? 1 : 0; }
+int altro_b200_is_supported(int n, int m, int model) { return lookup_ops(n, m, model, kPhasedTile, nullptr) ? 1 : 0; }
 
 // ---------------------------------------------------------------- problem
 int altro_b200_problem_create(int n, int m, int N, altro_b200_problem** out) {
@@ -671,6 +743,11 @@ int altro_b200_problem_add_control_bound(altro_b200_problem* p, int k, const dou
   b.kind = kControlBound;
   b.equality = 0;
   int row = 0;
+  {
+    int finite = 0;
+    for (int i = 0; i < p->m; ++i) finite += (std::fabs(lb[i]) < DBL_MAX) + (std::fabs(ub[i]) < DBL_MAX);
+    if (finite > kMaxDim) return fail(ALTRO_B200_ERR_UNSUPPORTED, "too many bound rows");
+  }
   for (int i = 0; i < p->m; ++i) {
     if (lb[i] > ub[i]) return fail(ALTRO_B200_ERR_ARG, "Lower bound isn't less than the upper bound.");
     if (std::fabs(lb[i]) < DBL_MAX) {  // basic_constraints.hpp:136-143
@@ -688,7 +765,6 @@ int altro_b200_problem_add_control_bound(altro_b200_problem* p, int k, const dou
     }
   b.nu = row - b.nl;
   b.p = row;
-  if (row > kMaxDim) return fail(ALTRO_B200_ERR_UNSUPPORTED, "too many bound rows");
   p->ineq[k].push_back(b);
   return 0;
 }
@@ -722,7 +798,7 @@ int altro_b200_problem_set_initial_state(altro_b200_problem* p, const double* x0
 int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_constraints, int device,
                              altro_b200_solver** out) {
   if (!p || !out || batch <= 0) return fail(ALTRO_B200_ERR_ARG, "solver_create: bad argument");
-  if (!lookup_ops(p->n, p->m, p->model, 32, nullptr))
+  if (!lookup_ops(p->n, p->m, p->model, kPhasedTile, nullptr))
     return fail(ALTRO_B200_ERR_UNSUPPORTED, "no device instantiation for (n=" + std::to_string(p->n) + ", m=" +
                                                std::to_string(p->m) + ", model=" + std::to_string(p->model) + ")");
   int ndev = 0;
@@ -735,10 +811,13 @@ int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_con
   DeviceGuard guard(device);
   int sm_count = 148;
   cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device);
-  auto s = std::make_unique<altro_b200_solver>();
+  // any failure below (typically cudaMalloc running out of memory at a large batch) releases what
+  // was allocated so far: the handle is destroyed through the public destructor
+  std::unique_ptr<altro_b200_solver, void (*)(altro_b200_solver*)> s(new altro_b200_solver(), altro_b200_solver_destroy);
+  s->device = device;
   s->n = p->n; s->m = p->m; s->N = p->N; s->B = batch;
   Ops probe;
-  lookup_ops(p->n, p->m, p->model, 32, &probe);
+  lookup_ops(p->n, p->m, p->model, kPhasedTile, &probe);
   if (probe.large && pmax > 0)
     return fail(ALTRO_B200_ERR_UNSUPPORTED, "the large-state path (n=32) supports unconstrained problems only");
   if (probe.large && static_cast<int>(p->params.size()) != p->n * (p->n + p->m))
@@ -814,9 +893,6 @@ void altro_b200_solver_destroy(altro_b200_solver* s) {
       if (w.P.Z[zb]) cudaFree(w.P.Z[zb]);
   if (s->d_io) cudaFree(s->d_io);
   if (s->h_count) cudaFreeHost(s->h_count);
-  if (s->st2) cudaStreamDestroy(s->st2);
-  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-  if (s->ev_join) cudaEventDestroy(s->ev_join);
   delete s;
 }
 
@@ -906,6 +982,14 @@ static int ensure_secondary(altro_b200_solver* s, int which) {
   if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.sc), static_cast<size_t>(S_NUM) * cap * sizeof(double)))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.is), static_cast<size_t>(I_NUM) * cap * sizeof(int)))) return rc;
   if ((rc = s->alloc(reinterpret_cast<void**>(&w.P.counters), 8 * sizeof(int)))) return rc;
+  // defined contents for the padding lanes of the last tile (they are staged, never used)
+  const int fill = std::getenv("ALTRO_B200_POISON") ? 0xFF : 0;
+  cudaMemset(w.P.KD, fill, knots * nkd);
+  if (s->pmax > 0) cudaMemset(w.P.LAM, fill, knots * s->pmax);
+  cudaMemset(w.P.X0, fill, static_cast<size_t>(cap) * s->n * sizeof(double));
+  cudaMemset(w.P.sc, 0, static_cast<size_t>(S_NUM) * cap * sizeof(double));
+  cudaMemset(w.P.is, 0, static_cast<size_t>(I_NUM) * cap * sizeof(int));
+  cudaDeviceSynchronize();  // the legacy-stream memsets above are not ordered with a non-blocking user stream
   w.allocated = true;
   return 0;
 }
@@ -917,6 +1001,7 @@ static int ensure_secondary_buffers(altro_b200_solver* s, int which, int nbuf, i
   altro_b200_solver::Secondary& w = s->sec[which];
   const size_t need = static_cast<size_t>(count) + kWarp;
   const size_t per_instance = static_cast<size_t>(s->N + 1) * (s->n + s->m) * sizeof(double);
+  bool fresh = false;
   for (int zb = 0; zb < nbuf; ++zb) {
     if (w.P.Z[zb] && w.zcap[zb] >= need) continue;
     if (w.P.Z[zb]) {
@@ -931,8 +1016,12 @@ static int ensure_secondary_buffers(altro_b200_solver* s, int which, int nbuf, i
     }
     w.zcap[zb] = need;
     s->dev_bytes += need * per_instance;
-    cudaMemset(w.P.Z[zb], 0, need * per_instance);
+    cudaMemset(w.P.Z[zb], std::getenv("ALTRO_B200_POISON") ? 0xFF : 0, need * per_instance);
+    fresh = true;
   }
+  // cudaMemset runs on the legacy default stream, which a non-blocking user stream does not wait
+  // for: without this the memset could land AFTER the re-pack kernel queued next on the solve's stream
+  if (fresh) cudaDeviceSynchronize();
   return 0;
 }
 
@@ -1005,13 +1094,16 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
   if (cur_sec >= 0 && (rc = scatter_back(*cur))) return rc;
   return 0;
 }
-// The same solve on the phased engine (phased.cuh): every slot is k_solve(outer/start parts) ->
-// expansions -> TMA-streamed backward pass -> wide line search -> deep line search, all queued
-// on the stream without host round trips; every `poll` slots the host reads the unfinished
-// count and, when enough instances are done, re-packs the rest densely.
+// The same solve on the phased engine: every slot is [outer-step kernels on a dense list
+// (outer.cuh)] -> expansions -> TMA-streamed backward pass -> wide line search -> deep line
+// search, all queued on ONE stream without host round trips; every `poll` slots the host reads
+// the unfinished count and, when enough instances are done, re-packs the rest densely.
 static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
   DeviceGuard guard(s->device);
-  const int outer_period = std::max(1, env_int("ALTRO_B200_OUTER_PERIOD", 4));
+  // Outer steps cost ~0.1 ms whatever the number of instances taking one (two serial chains over
+  // the horizon): they run every outer_period slots; an instance that ended an iLQR solve waits
+  // for the next one (results do not depend on when it is served).
+  const int outer_period = std::max(1, env_int("ALTRO_B200_OUTER_PERIOD", 2));
   const int poll = outer_period * std::max(1, env_int("ALTRO_B200_POLL", 4) / outer_period);
   const int repack_pct = env_int("ALTRO_B200_REPACK_PCT", 70);  // 0 disables re-packing
   int rc;
@@ -1035,55 +1127,33 @@ static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
     if (e_ != cudaSuccess)                                                                 \
       return fail(ALTRO_B200_ERR_CUDA, std::string(what " launch: ") + cudaGetErrorString(e_)); \
   } while (0)
-  // Overlapping the outer-step kernel with the inner-iteration kernels on a second stream is worth
-  // ~12 % on C2, but re-solves were observed not to be bit-reproducible with it at B = 16384 (one
-  // tile in ~10^4 differs in the last bits; tools/gpu_determinism.py) although the two kernel groups
-  // own disjoint instances.  Until that is understood it is opt-in: ALTRO_B200_OVERLAP=1.
-  const bool overlap = env_int("ALTRO_B200_OVERLAP", 0) != 0;
-  if (overlap && !s->st2) {
-    CU(cudaStreamCreateWithFlags(&s->st2, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
-  }
-  const int lsmode = mode | (overlap ? 2 : 0);
   // the split line search evaluates the tries in two rounds (32/W, then 32): longer searches use
   // the fused line-search kernels, which loop
   // ... and only pays when few instances are in flight (the slot is then bound by the length of
   // the serial chains, not by instruction throughput)
-  const int split_max = env_int("ALTRO_B200_SPLIT_MAX", 2048);
+  const int split_max = std::min(env_split_max(), s->P.split_cap);
   const bool split_ok = s->P.opt.line_search_max_iterations <= kWarp / kPhasedTile + kWarp;
   for (long slot = 0; slot < 10000000; ++slot) {
     cur->opt = s->P.opt;
     CU(cudaMemsetAsync(cur->counters, 0, 8 * sizeof(int), st));
     const bool polling = (slot % poll) == 0;
-    if (overlap) {
-      // outer steps / solve starts / final costs on st2, concurrent with the inner iteration of
-      // the instances that were in kPhInner at the slot boundary
-      k_promote<<<(cur->B + 255) / 256, 256, 0, st>>>(*cur);
-      if ((rc = check_launch(s, 1))) return rc;
-      CU(cudaEventRecord(s->ev_fork, st));
-      CU(cudaStreamWaitEvent(s->st2, s->ev_fork, 0));
-      PH(cur_ops.solve(*cur, mode, 1, 1 | 4, s->st2), "k_solve");
-      if (polling) CU(cudaMemcpyAsync(s->h_count, cur->counters, sizeof(int), cudaMemcpyDeviceToHost, s->st2));
-      CU(cudaEventRecord(s->ev_join, s->st2));
-    } else if (slot % outer_period == 0) {
-      // outer steps are serial chains over the horizon whatever the number of instances taking one:
-      // they are batched every outer_period slots (an instance that ended an iLQR solve waits for
-      // the next batch; results do not depend on when it is served)
-      PH(cur_ops.solve(*cur, mode, 1, 1, st), "k_solve");
+    if (slot % outer_period == 0) {
+      int nl = 0;
+      cudaError_t e = cur_ops.outer_step(*cur, mode, s->sm_count, st, &nl);
+      s->launches += nl;
+      if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("outer-step launch: ") + cudaGetErrorString(e));
       if (polling) CU(cudaMemcpyAsync(s->h_count, cur->counters, sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     PH(cur_ops.expansions_phased(*cur, st), "k_update_expansions");
     PH(cur_ops.backward_phased(*cur, st), "k_backward_mat");
     if (split_ok && cur->B <= split_max) {
-      PH(cur_ops.ls_split_wide(*cur, lsmode, st), "k_roll/cost/acc_wide");
-      PH(cur_ops.ls_split_deep(*cur, lsmode, cur->B, st), "k_roll/cost/acc_deep");
+      PH(cur_ops.ls_split_wide(*cur, mode, st), "k_roll/cost/acc_wide");
+      PH(cur_ops.ls_split_deep(*cur, mode, cur->B, st), "k_roll/cost/acc_deep");
       s->launches += 4;
     } else {
-      PH(cur_ops.ls_wide(*cur, lsmode, st), "k_ls_wide");
-      PH(cur_ops.ls_deep(*cur, lsmode, cur->B, st), "k_ls_deep");
+      PH(cur_ops.ls_wide(*cur, mode, st), "k_ls_wide");
+      PH(cur_ops.ls_deep(*cur, mode, cur->B, st), "k_ls_deep");
     }
-    if (overlap) CU(cudaStreamWaitEvent(st, s->ev_join, 0));
     if (!polling) continue;
     CU(cudaStreamSynchronize(st));
     const int unfinished = s->h_count[0];
@@ -1103,8 +1173,8 @@ static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
       Q.Bp = Q.T * Q.W;
       Q.N = s->N; Q.n = s->n; Q.m = s->m; Q.pmax = s->pmax; Q.use_al = s->use_al;
       Q.blob = s->P.blob; Q.blob_bytes = s->P.blob_bytes;
-      Q.EXP = s->P.EXP; Q.CAND = s->P.CAND; Q.list = s->P.list;  // per-slot scratch, shared
-      Q.COSTK = s->P.COSTK; Q.TRYST = s->P.TRYST;
+      Q.EXP = s->P.EXP; Q.CAND = s->P.CAND; Q.list = s->P.list; Q.olist = s->P.olist;  // per-slot scratch, shared
+      Q.COSTK = s->P.COSTK; Q.TRYST = s->P.TRYST; Q.split_cap = s->P.split_cap;
       lookup_ops(s->n, s->m, s->model, Q.W, &w.ops);
       dim3 grid((unfinished + 127) / 128, s->N + 2);
       k_move_instances<<<grid, 128, 0, st>>>(*cur, Q, s->d_list, unfinished, 0);
@@ -1123,6 +1193,7 @@ static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
 static int solve_dispatch(altro_b200_solver* s, int mode, cudaStream_t st) {
   if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
   if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
+  s->expansions_valid = false;  // the phased engine uses EXP as per-slot scratch
   if (s->engine == ALTRO_B200_ENGINE_PHASED && s->ops.ls_wide) return solve_phased_impl(s, mode, st);
   return solve_impl(s, mode, st);
 }
@@ -1190,12 +1261,22 @@ int altro_b200_update_expansions(altro_b200_solver* s, void* stream) {
   cudaError_t e = s->ops.expansions(s->P, S(stream));
   s->launches += 1;
   if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("k_update_expansions launch: ") + cudaGetErrorString(e));
+  s->expansions_valid = true;
+  s->insolve_ready = false;
   return 0;
 }
 int altro_b200_backward_pass(altro_b200_solver* s, void* stream) {
   if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
-  if (!s->P.EXP) return fail(ALTRO_B200_ERR_STATE, "UpdateExpansions must run before BackwardPass");
+  if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
+  if (s->ops.large) return fail(ALTRO_B200_ERR_UNSUPPORTED, "step-wise methods are not available on the large-state path");
+  // the records of a whole solve's last slot are not the expansion of the current Z_ (and the phased
+  // engine's scratch has no cost-to-go / costs_ arrays): require an explicit UpdateExpansions
+  if (!s->expansions_valid) return fail(ALTRO_B200_ERR_STATE, "UpdateExpansions must run before BackwardPass");
   DeviceGuard guard(s->device);
+  {
+    int rc = s->ensure_stepwise();
+    if (rc) return rc;
+  }
   cudaError_t e = s->ops.backward_mat(s->P, /*store_ctg=*/true, S(stream));
   s->launches += 1;
   if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("backward_pass: ") + cudaGetErrorString(e));
@@ -1212,9 +1293,29 @@ int altro_b200_update_penalties(altro_b200_solver* s, void* stream) {
 
 // Measurement entry points (not part of the reference surface): the bare kernels.
 int altro_b200_backward_pass_stream_only(altro_b200_solver* s, void* stream) {
-  if (!s || !s->P.EXP) return fail(ALTRO_B200_ERR_STATE, "UpdateExpansions must run before BackwardPass");
+  if (!s || !s->expansions_valid) return fail(ALTRO_B200_ERR_STATE, "UpdateExpansions must run before BackwardPass");
   DeviceGuard guard(s->device);
   cudaError_t e = s->ops.backward_mat(s->P, /*store_ctg=*/false, S(stream));
+  s->launches += 1;
+  if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("backward_pass: ") + cudaGetErrorString(e));
+  return 0;
+}
+// The backward-pass kernel exactly as the phased engine launches it inside a solve
+// (k_backward_mat<..., kPhased = true>: per-instance phase mask, regularisation hand-off, list of
+// stalled instances), on the records of the last UpdateExpansions with EVERY instance marked as
+// being in an inner iteration.  Scrambles the solve state: set the inputs again afterwards.
+int altro_b200_backward_pass_insolve(altro_b200_solver* s, void* stream) {
+  if (!s || !s->expansions_valid) return fail(ALTRO_B200_ERR_STATE, "UpdateExpansions must run before BackwardPass");
+  if (!s->ops.backward_phased) return fail(ALTRO_B200_ERR_UNSUPPORTED, "no phased engine for this solver");
+  DeviceGuard guard(s->device);
+  int rc;
+  if ((rc = s->ensure_phased())) return rc;
+  if (!s->insolve_ready) {  // once per UpdateExpansions: the timed launches are the kernel alone
+    if ((rc = fill_int(s, I_PHASE, kPhInner, S(stream)))) return rc;
+    if ((rc = fill_int(s, I_LSFAIL, 0, S(stream)))) return rc;
+    s->insolve_ready = true;
+  }
+  cudaError_t e = s->ops.backward_phased(s->P, S(stream));
   s->launches += 1;
   if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("backward_pass: ") + cudaGetErrorString(e));
   return 0;

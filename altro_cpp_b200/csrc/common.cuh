@@ -53,6 +53,13 @@ enum BlockShape : int {
   kShapeCirclesOneChunk = 2,   // circle block with at most 4 circles
 };
 
+// Shapes of a QuadraticCost the device code has shorter paths for (same sums, the exact-zero terms
+// dropped); detected when the blob is built and stored in the last slot of the cost record.
+enum CostShape : int {
+  kCostDense = 0,
+  kCostDiagonal = 1,  // Q and R diagonal, H = 0 (what QuadraticCost::LQRCost builds from diagonal weights)
+};
+
 // One ConstraintValues<n,m,ConType> (altro/constraints/constraint_values.hpp:24) of a knot.
 struct ConBlock {
   int kind;      // ConKind
@@ -84,7 +91,7 @@ struct ConSet {
 struct BlobHeader {
   int n, m, N, model;
   int ncost, nconset, pmax, nparams;
-  int cost_stride;     // doubles per QuadraticCost: n*n + m*m + n*m + n + m + 1
+  int cost_stride;     // doubles per QuadraticCost: n*n + m*m + n*m + n + m + 1, + 1 slot holding the CostShape
   int off_cost_id;     // int[N+1]: byte offset (from the blob base) of knot k's QuadraticCost
   int off_conset_id;   // int[N+1]: byte offset of knot k's ConSet
   int off_h;           // float[N+1]
@@ -162,7 +169,8 @@ enum ScalarField : int {
   S_CSRC_ALPHA,    // Q8: < 0 -> stored constraint values come from Z; else alpha of the last
                    //        evaluated (rejected) candidate
   S_J0,            // costs_.sum() of the current Z_ (carried between launches of k_solve)
-  S_GS_BWD,        // sum_k max_i |d_i|/(|u_i|+1) of the last backward pass (phased engine hand-off)
+  S_VTMP,          // phased engine scratch: bit pattern of a running max violation (atomicMax on the
+                   // unsigned view of non-negative doubles: exact and order-independent)
   S_REG_IN, S_DREG_IN,  // regularisation at the entry of the current inner iteration (phased engine hand-off)
   S_NUM
 };
@@ -187,12 +195,6 @@ enum SolvePhase : int {
   kPhDone = 4,        // terminated; final Cost() not reported yet
   kPhReported = 5,    // everything written
   kPhMoved = 6,       // continued in another workspace
-  // phased engine, overlapped mode: the outer-step kernel of a slot runs concurrently with the
-  // inner-iteration kernels of the other instances; a transition made during a slot becomes
-  // visible to the other kernel group only at the next slot boundary (k_promote)
-  kPhInnerPending = -1,
-  kPhOuterPending = -2,
-  kPhDonePending = -3,
 };
 
 struct SolverParams {
@@ -210,13 +212,17 @@ struct SolverParams {
   double* COSTS;  // [T][N+1][W]            costs_ vector (step-wise API only)
   double* sc;     // [S_NUM][Bp]
   int* is;        // [I_NUM][Bp]
-  int* counters;  // [0] = instances not yet reported after the last k_solve launch; [1],[2] re-pack
-                  // cursors; [3] = entries of `list` (phased engine); 8 ints
+  int* counters;  // [0] = instances not yet reported after the last k_solve launch / outer step; [1],[2]
+                  // re-pack cursors; [3] = entries of `list`; [4] = entries of `olist` (phased engine); 8 ints
   int* list;      // [Bp] phased engine: instances whose line search continues in k_ls_deep
-  double* CAND;   // [Bp][N+1][n+m][32]  phased engine: candidate trajectories of k_ls_deep (scratch)
-  double* COSTK;  // [Bp][N+1][32]  phased engine: per-knot costs of line-search candidates (scratch),
-                  //                row = tile (wide kernels) or list entry (deep kernels), lane fastest
-  int* TRYST;     // [Bp][32]       phased engine: status left by each candidate rollout
+  int* olist;     // [Bp] phased engine: instances with outer-loop work pending (outer.cuh)
+  double* CAND;   // [cap][N+1][n+m][32]  phased engine, split line search: candidate trajectories of
+                  //                k_roll_deep (scratch), cap = split_cap list entries
+  double* COSTK;  // [rows][N+1][32]  phased engine: per-knot costs of line-search candidates (scratch),
+                  //                row = tile (wide kernels) or list entry (deep kernels), lane fastest;
+                  //                also [entry][N+1] per-knot costs of the outer-step kernels
+  int* TRYST;     // [rows][32]     phased engine: status left by each candidate rollout
+  int split_cap;  // list entries CAND / COSTK / TRYST have room for in the split deep kernels
   DevOptions opt;
 };
 

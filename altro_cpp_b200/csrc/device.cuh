@@ -299,9 +299,31 @@ __device__ __forceinline__ void rk4_jacobian(const double* P, const double* x, c
 // ------------------------------------------------------------------------------------------
 // QuadraticCost (examples/quadratic_cost.cpp:8-28).  C = [Q (n*n), R (m*m), H (n*m), q, r, c].
 // ------------------------------------------------------------------------------------------
+// shape of the cost record (CostShape), stored as a double in the slot after c
+template <int n, int m>
+__device__ __forceinline__ int quad_shape(const double* C) {
+  return static_cast<int>(C[n * n + m * m + n * m + n + m + 1]);
+}
+
 template <int n, int m>
 __device__ __forceinline__ double quad_eval(const double* C, const double* x, const double* u) {
   const double *Q = C, *R = C + n * n, *H = R + m * m, *q = H + n * m, *r = q + n;
+  if (quad_shape<n, m>(C) == kCostDiagonal) {
+    // the dense sums below with their exact-zero products left out: Qx_i = Q_ii x_i, Hu = 0, Ru_i = R_ii u_i
+    double xQx = x[0] * (Q[0] * x[0]), qx = q[0] * x[0];
+    ALTRO_UNROLL
+    for (int i = 1; i < n; ++i) {
+      xQx += x[i] * (Q[i + i * n] * x[i]);
+      qx += q[i] * x[i];
+    }
+    double uRu = u[0] * (R[0] * u[0]), ru = r[0] * u[0];
+    ALTRO_UNROLL
+    for (int i = 1; i < m; ++i) {
+      uRu += u[i] * (R[i + i * m] * u[i]);
+      ru += r[i] * u[i];
+    }
+    return 0.5 * xQx + 0.5 * uRu + qx + ru + r[m];
+  }
   double Qx[n], Hu[n], Ru[m];
   ALTRO_UNROLL
   for (int i = 0; i < n; ++i) {
@@ -341,6 +363,15 @@ template <int n, int m>
 __device__ __forceinline__ void quad_gradient(const double* C, const double* x, const double* u,
                                               double* dx, double* du) {
   const double *Q = C, *R = C + n * n, *H = R + m * m, *q = H + n * m, *r = q + n;
+  if (quad_shape<n, m>(C) == kCostDiagonal) {
+    // product and sum rounded separately, as in the dense path (where the product is the tail of
+    // a sum of exact zeros and cannot fuse with the addition of q_i)
+    ALTRO_UNROLL
+    for (int i = 0; i < n; ++i) dx[i] = __dadd_rn(__dmul_rn(Q[i + i * n], x[i]), q[i]);
+    ALTRO_UNROLL
+    for (int i = 0; i < m; ++i) du[i] = __dadd_rn(__dmul_rn(R[i + i * m], u[i]), r[i]);
+    return;
+  }
   ALTRO_UNROLL
   for (int i = 0; i < n; ++i) {
     double a = Q[i] * x[0];

@@ -607,8 +607,7 @@ __device__ __forceinline__ void finish_inner(const DevOptions& o, int N, int mod
                                              double initial_cost, double& alpha_stat, double& z_stat,
                                              double& csrc, double& grad, double& dJ, double& reg,
                                              double& dreg, int& it_inner, int& it_total, int& st,
-                                             int& phase, int& lsfail, int ph_outer = kPhOuter,
-                                             int ph_done = kPhDone) {
+                                             int& phase, int& lsfail) {
   lsfail = t.success ? 0 : 1;
   if (t.success) {
     zsel = t.new_zsel;  // (*Z_) = (*Zbar_)
@@ -655,7 +654,7 @@ __device__ __forceinline__ void finish_inner(const DevOptions& o, int N, int mod
     }
     done = true;
   }
-  if (done) phase = (mode == 1) ? ph_outer : ph_done;
+  if (done) phase = (mode == 1) ? kPhOuter : kPhDone;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -669,13 +668,11 @@ __device__ __forceinline__ void finish_inner(const DevOptions& o, int N, int mod
 // ------------------------------------------------------------------------------------------
 constexpr int kSolveWarps = ALTRO_SOLVE_WARPS;
 
-// kParts: compile-time mask on `parts` (1 outer step + solve start, 2 inner iteration, 4 overlapped
-// mode).  The phased engine instantiates kParts = 5: the inner iteration is compiled out, which
-// leaves a small kernel without register spills for the outer steps.
-template <class M, int W, int kParts = 7>
-__global__ void __launch_bounds__(kSolveWarps* kWarp, ((W <= 4 || (kParts & 2) == 0) ? ALTRO_SOLVE_MINB_NARROW : ALTRO_SOLVE_MINB)) k_solve(SolverParams P, int mode,
-                                                                               int budget, int parts_rt) {
-  const int parts = parts_rt & kParts;
+// parts: 1 = outer step + solve start, 2 = inner iteration (3 = everything; the step-wise tests
+// run the halves separately).
+template <class M, int W>
+__global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB_NARROW : ALTRO_SOLVE_MINB)) k_solve(SolverParams P, int mode,
+                                                                               int budget, int parts) {
   extern __shared__ __align__(128) char smem[];
   copy_blob(P.blob, smem, P.blob_bytes);
   const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -722,10 +719,6 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, ((W <= 4 || (kParts & 2) =
     lsfail = L.is(I_LSFAIL);
   }
   const bool was_reported = phase >= kPhReported;
-  // overlapped mode of the phased engine (parts & 4): instances in kPhInner belong to the
-  // inner-iteration kernels running concurrently on another stream — hands off their state
-  // (a pending phase seen here was written during this slot by those kernels: still theirs)
-  const bool foreign = (parts & 4) && (phase == kPhInner || phase < 0);
   if (phase == kPhAlInit) {  // AugmentedLagrangianiLQR::Init, al_solver.hpp:287-302 (Q10)
     if (o.reset_duals && has_con && L.a == 0) {
       for (int k = 0; k <= N; ++k) {
@@ -803,8 +796,7 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, ((W <= 4 || (kParts & 2) =
         J0 = Jr;
         initial_cost = Jr;
         csrc = -1.0;
-        phase = (o.max_iterations_inner > 0) ? ((parts & 4) ? kPhInnerPending : kPhInner)
-                                             : (mode == 1 ? kPhOuter : kPhDone);
+        phase = (o.max_iterations_inner > 0) ? kPhInner : (mode == 1 ? kPhOuter : kPhDone);
       }
     }
     // ------------- one inner iteration, ilqr.hpp:300-313 ------------------------------------
@@ -843,8 +835,7 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, ((W <= 4 || (kParts & 2) =
   const bool fin = phase == kPhDone;
   double Jf = 0.0, vf = 0.0;
   if (__any_sync(kFull, fin)) Jf = sweep_cost<M, W, false>(L, stg, fin && L.a == 0, zsel, penalty, &vf);
-  if (lead && !was_reported && foreign) atomicAdd(&P.counters[0], 1);
-  if (lead && !was_reported && !foreign) {
+  if (lead && !was_reported) {
     if (fin) {
       if (mode == 0) viol = vf;  // == Cost(); GetMaxViolation()
       L.sc(S_COST) = Jf;
@@ -895,17 +886,6 @@ __global__ void k_list_unfinished(SolverParams src, int* __restrict__ list, int 
       list[total - 1 - atomicAdd(&src.counters[2], 1)] = b;
     }
   }
-}
-
-// slot boundary of the phased engine in overlapped mode: pending transitions take effect
-__global__ void k_promote(SolverParams P) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= P.B) return;
-  int& ph = P.is[static_cast<size_t>(I_PHASE) * P.Bp + b];
-  const int v = ph;
-  if (v == kPhInnerPending) ph = kPhInner;
-  else if (v == kPhOuterPending) ph = kPhOuter;
-  else if (v == kPhDonePending) ph = kPhDone;
 }
 
 // dst slot j <- src slot list[j]: current trajectory (into buffer 0), gains, duals, x0, scalars.
@@ -1139,33 +1119,42 @@ __global__ void __launch_bounds__(128, ALTRO_EXP_MINB) k_update_expansions(Solve
   for (int q = 0; q < n; ++q) x[q] = zc[q * W];
   ALTRO_UNROLL
   for (int q = 0; q < m; ++q) u[q] = zc[(n + q) * W];
-  double A[n * n], B[n * m], lxx[n * n], lxu[n * m], luu[m * m], lx[n], lu[m];
-  ALTRO_UNROLL
-  for (int q = 0; q < n * n; ++q) A[q] = 0.0;
-  ALTRO_UNROLL
-  for (int q = 0; q < n * m; ++q) B[q] = 0.0;
-  if (k == P.N) {  // IdentityDynamics::Jacobian, problem.hpp:40-43: setIdentity on n x (n+m)
-    ALTRO_UNROLL
-    for (int q = 0; q < n; ++q) A[q + q * n] = 1.0;
-  }
   const double* lam = P.pmax > 0 ? L.lam(k) : nullptr;
-  knot_expansion<M, W>(L.D, P.N, k, x, u, lam, penalty, A, B, lxx, lxu, luu, lx, lu);
   double* e = L.exp(k);
-  int f = 0;
-  ALTRO_UNROLL
-  for (int q = 0; q < n * n; ++q) e[(f++) * W] = A[q];
-  ALTRO_UNROLL
-  for (int q = 0; q < n * m; ++q) e[(f++) * W] = B[q];
-  ALTRO_UNROLL
-  for (int q = 0; q < n * n; ++q) e[(f++) * W] = lxx[q];
-  ALTRO_UNROLL
-  for (int q = 0; q < n * m; ++q) e[(f++) * W] = lxu[q];
-  ALTRO_UNROLL
-  for (int q = 0; q < m * m; ++q) e[(f++) * W] = luu[q];
-  ALTRO_UNROLL
-  for (int q = 0; q < n; ++q) e[(f++) * W] = lx[q];
-  ALTRO_UNROLL
-  for (int q = 0; q < m; ++q) e[(f++) * W] = lu[q];
+  constexpr int off_cost = n * n + n * m;  // record: [A | B | lxx | lxu | luu | lx | lu]
+  {
+    // cost / constraint expansion first, written out before the dynamics Jacobian is formed: the two
+    // halves never hold their registers at the same time
+    double lxx[n * n], lxu[n * m], luu[m * m], lx[n], lu[m], dA[1], dB[1];
+    knot_expansion<M, W, false>(L.D, P.N, k, x, u, lam, penalty, dA, dB, lxx, lxu, luu, lx, lu);
+    int f = off_cost;
+    ALTRO_UNROLL
+    for (int q = 0; q < n * n; ++q) e[(f++) * W] = lxx[q];
+    ALTRO_UNROLL
+    for (int q = 0; q < n * m; ++q) e[(f++) * W] = lxu[q];
+    ALTRO_UNROLL
+    for (int q = 0; q < m * m; ++q) e[(f++) * W] = luu[q];
+    ALTRO_UNROLL
+    for (int q = 0; q < n; ++q) e[(f++) * W] = lx[q];
+    ALTRO_UNROLL
+    for (int q = 0; q < m; ++q) e[(f++) * W] = lu[q];
+  }
+  {
+    double A[n * n], B[n * m];
+    if (k < P.N) {
+      rk4_jacobian<M>(L.D.params(), x, u, L.D.h(k), A, B);
+    } else {  // IdentityDynamics::Jacobian, problem.hpp:40-43: setIdentity on n x (n+m)
+      ALTRO_UNROLL
+      for (int q = 0; q < n * n; ++q) A[q] = (q % (n + 1) == 0) ? 1.0 : 0.0;
+      ALTRO_UNROLL
+      for (int q = 0; q < n * m; ++q) B[q] = 0.0;
+    }
+    int f = 0;
+    ALTRO_UNROLL
+    for (int q = 0; q < n * n; ++q) e[(f++) * W] = A[q];
+    ALTRO_UNROLL
+    for (int q = 0; q < n * m; ++q) e[(f++) * W] = B[q];
+  }
   if (!kPhased) {
     // costs_(k) = Cost(x,u), ilqr.hpp:675
     *L.costs(k) = knot_cost<n, m, W>(L.D, k, x, u, lam, AlPen(penalty), nullptr);
@@ -1237,9 +1226,10 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 // a kStages-deep shared-memory ring by TMA bulk copies (one per tile per knot) issued by lane 0
 // and tracked with mbarriers; every lane then reads its own column (conflict-free) and runs the
 // Riccati step in registers.  Writes K, d (and P, p when kStoreCtg).
-// kPhased: only instances in kPhInner run; additionally hands sum_k max_i |d_i|/(|u_i|+1) and
-// the entry regularisation to the line-search kernels and lists the instances whose previous
-// search failed completely for k_ls_deep (phased.cuh).
+// kPhased: only instances in kPhInner run; additionally hands the entry regularisation to the
+// line-search kernels (phased.cuh).  The kernel touches nothing but the records, K, d and a few scalars per
+// instance: the gain statistic of a failed search (sum_k max_i |d_i|/(|u_i|+1), which needs the
+// controls) is formed by the line-search kernel that observes the failure.
 template <class M, int W, int kStages, bool kStoreCtg, bool kPhased = false>
 __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
   constexpr int n = M::n, m = M::m, nexp = Lane<M, W>::nexp, TPW = kWarp / W;
@@ -1256,8 +1246,6 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
   const int N = P.N;
   const bool valid = L.valid && (!kPhased || L.is(I_PHASE) == kPhInner);
   if (kPhased && !__any_sync(kFull, valid)) return;
-  const int zsel = (kPhased && valid) ? L.is(I_ZSEL) : 0;
-  double gs = 0.0;
   if (lane == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1284,7 +1272,6 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
   bool repeat = valid;
   uint32_t issued = 0, consumed = 0;  // monotonically increasing slot counters (warp-uniform)
   while (__any_sync(kFull, repeat)) {
-    gs = 0.0;
     // terminal cost-to-go: lxx, lx of knot N (plain loads, once per pass)
     double Pm[n * n], p[n];
     {
@@ -1307,14 +1294,6 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
     for (int s = 0; s < kStages && next_k >= 0; ++s, --next_k, ++issued)
       if (lane == 0) load_slot(issued % kStages, next_k);
     bool live = repeat;  // lanes still descending in this pass
-    double uk_next[m];
-    ALTRO_UNROLL
-    for (int q = 0; q < m; ++q) uk_next[q] = 0.0;
-    if (kPhased && live) {
-      const double* zc = L.z(zsel, N - 1);
-      ALTRO_UNROLL
-      for (int q = 0; q < m; ++q) uk_next[q] = zc[(n + q) * W];
-    }
     for (int k = N - 1; k >= 0; --k, ++consumed) {
       const int slot = consumed % kStages;
       mbar_wait(&bars[slot], (consumed / kStages) & 1);
@@ -1342,16 +1321,7 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
         ++issued;
       }
       if (live) {
-        double K[m * n], d[m], uk[m];
-        if (kPhased) {  // controls of this knot were requested one knot ago; request the next ones
-          ALTRO_UNROLL
-          for (int q = 0; q < m; ++q) uk[q] = uk_next[q];
-          if (k > 0) {
-            const double* zc = L.z(zsel, k - 1);
-            ALTRO_UNROLL
-            for (int q = 0; q < m; ++q) uk_next[q] = zc[(n + q) * W];
-          }
-        }
+        double K[m * n], d[m];
         const bool ok =
             riccati_step<n, m>(A, B, lxx, lxu, luu, lx, lu, Pm, p, reg, K, d, &dV0, &dV1);
         if (!ok) {  // ilqr.hpp:409-427: raise the regularisation, restart from k = N-1
@@ -1368,12 +1338,6 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
           for (int q = 0; q < m * n; ++q) pk[q * W] = K[q];
           ALTRO_UNROLL
           for (int q = 0; q < m; ++q) pk[(m * n + q) * W] = d[q];
-          if (kPhased) {
-            double g = fabs(d[0]) / (fabs(uk[0]) + 1);
-            ALTRO_UNROLL
-            for (int q = 1; q < m; ++q) g = fmax(g, fabs(d[q]) / (fabs(uk[q]) + 1));
-            gs += g;
-          }
           if (kStoreCtg) {
             double* c = L.ctg(k);
             ALTRO_UNROLL
@@ -1394,10 +1358,8 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
     L.sc(S_DV1) = dV1;
     L.is(I_STATUS) = st;
     if (kPhased) {
-      L.sc(S_GS_BWD) = gs;
       L.sc(S_REG_IN) = reg_in;
       L.sc(S_DREG_IN) = dreg_in;
-      if (L.is(I_LSFAIL) != 0) P.list[atomicAdd(&P.counters[3], 1)] = L.b << 1;
     }
   }
 }

@@ -65,7 +65,10 @@ __host__ __device__ constexpr int p_stage_doubles(int pmax, int WI) {
 // Returns false when the state/control bound check trips (status is set like the reference).
 // kDbg (latency probe only, 0 in every solve kernel): 1 no cost, 2 no dynamics, 4 no staging
 // after knot 0, 8 no candidate stores, 16 no normalised-gain division
-template <class M, int W, int WI, int kDbg = 0>
+// kStore = false: the candidate is evaluated but not written anywhere (the deep search only needs
+// its cost; the winner is rolled out again to its destination).  kGain = false: no normalised
+// feed-forward gain (gsum = 0).
+template <class M, int W, int WI, int kDbg = 0, bool kStore = true, bool kGain = true>
 __device__ __forceinline__ bool p_rollout(const PLane<M, W, WI>& L, double* stg, bool active, int zsel,
                                           double* zo, int zrow, int zknot, double alpha, double penalty,
                                           double& J, double& gsum, int& status) {
@@ -91,6 +94,19 @@ __device__ __forceinline__ bool p_rollout(const PLane<M, W, WI>& L, double* stg,
           g = L.lam(k) + (r - off_lam) * W;
         }
         cp_async8(s + r, g);
+      }
+    } else if (WI <= 4) {  // few instances per warp: the G lanes of an instance share its rows
+      for (int r = L.a; r < R; r += PLane<M, W, WI>::G) {
+        const double* g;
+        if (r < nz) {
+          g = L.z(zsel, k) + r * W;
+        } else if (r < off_lam) {
+          if (k >= N) continue;
+          g = L.kd(k) + (r - nz) * W;
+        } else {
+          g = L.lam(k) + (r - off_lam) * W;
+        }
+        cp_async8(s + r * WI + L.si, g);
       }
     } else if (L.a == 0) {
       s += L.si;
@@ -138,14 +154,16 @@ __device__ __forceinline__ bool p_rollout(const PLane<M, W, WI>& L, double* stg,
           for (int j = 1; j < n; ++j) acc += s[(nz + q + j * m) * WI] * dx[j];
           const double dq = s[(nz + m * n + q) * WI];
           u[q] = s[(n + q) * WI] + acc + dq * alpha;  // ilqr.hpp:478
-          const double gq = (kDbg & 16) ? fabs(dq) : fabs(dq) / (fabs(u[q]) + 1);
-          g = (q == 0) ? gq : fmax(g, gq);
+          if (kGain) {
+            const double gq = (kDbg & 16) ? fabs(dq) : fabs(dq) / (fabs(u[q]) + 1);
+            g = (q == 0) ? gq : fmax(g, gq);
+          }
         }
       } else {  // terminal knot of Zbar: u_N = 0 (SetZero, Q14)
         ALTRO_UNROLL
         for (int q = 0; q < m; ++q) u[q] = 0.0;
       }
-      if (!(kDbg & 8)) {
+      if (kStore && !(kDbg & 8)) {
         ALTRO_UNROLL
         for (int q = 0; q < n; ++q) zn[q * zrow] = x[q];
         ALTRO_UNROLL
@@ -198,7 +216,7 @@ struct PLsResult {
   double J, alpha, z, gsum;
 };
 
-template <class M, int W, int WI>
+template <class M, int W, int WI, bool kStore = true>
 __device__ __forceinline__ PLsResult p_line_search(const PLane<M, W, WI>& L, double* stg, bool run, int zsel,
                                                    double* zo, int zrow, int zknot, double penalty,
                                                    double J0, double dV0, double dV1, int& status,
@@ -223,7 +241,8 @@ __device__ __forceinline__ PLsResult p_line_search(const PLane<M, W, WI>& L, dou
     const bool mine = searching && (done + L.a < o.line_search_max_iterations);
     double J = 0.0, gs = 0.0, z = -1.0;
     int st_try = status;
-    const bool ok = p_rollout<M, W, WI>(L, stg, mine, zsel, zo, zrow, zknot, alpha, penalty, J, gs, st_try);
+    const bool ok = p_rollout<M, W, WI, 0, kStore, kStore>(L, stg, mine, zsel, zo, zrow, zknot, alpha, penalty, J, gs,
+                                                           st_try);
     bool acc = false;
     if (mine && ok) {
       const double expected = -alpha * (dV0 + alpha * dV1);
@@ -276,11 +295,10 @@ __device__ __forceinline__ PLsResult p_line_search(const PLane<M, W, WI>& L, dou
 
 // Tail of the inner iteration for one instance (called by the lane that owns it): loads the rest
 // of the instance state, applies finish_inner and writes everything back.
+// gsum_bwd: sum_k max_i |d_i|/(|u_i|+1) over the current Z_ (only read when the search failed).
 template <class LaneT>
 __device__ __forceinline__ void p_finish(const LaneT& L, int mode, const PLsResult& r, int new_zsel, int zsel,
-                                         double J0, double csrc, int st) {
-  const bool pend = (mode & 2) != 0;  // overlapped mode: phase changes wait for the slot boundary
-  mode &= 1;
+                                         double J0, double csrc, int st, double gsum_bwd) {
   const DevOptions& o = L.P.opt;
   double cost_cur = L.sc(S_COST_CUR), cost_prev = L.sc(S_COST_PREV);
   const double initial_cost = L.sc(S_INITIAL_COST);
@@ -295,12 +313,11 @@ __device__ __forceinline__ void p_finish(const LaneT& L, int mode, const PLsResu
   t.alpha = r.alpha;
   t.z = r.z;
   t.gsum_ls = r.gsum;
-  t.gsum_bwd = L.sc(S_GS_BWD);
+  t.gsum_bwd = gsum_bwd;
   t.reg_in = L.sc(S_REG_IN);
   t.dreg_in = L.sc(S_DREG_IN);
   finish_inner(o, L.P.N, mode, t, zsel, J0, cost_cur, cost_prev, initial_cost, alpha_stat, z_stat, csrc, grad,
-               dJ, reg, dreg, it_inner, it_total, st, phase, lsfail, pend ? kPhOuterPending : kPhOuter,
-               pend ? kPhDonePending : kPhDone);
+               dJ, reg, dreg, it_inner, it_total, st, phase, lsfail);
   L.is(I_ZSEL) = zsel;
   L.sc(S_J0) = J0;
   L.sc(S_COST_CUR) = cost_cur;
@@ -453,6 +470,34 @@ __device__ __forceinline__ double knot_gain(const double* d, int ds, const doubl
   return g;
 }
 
+// sum_k max_i |d_i|/(|u_i|+1) over the CURRENT trajectory (Z_ in buffer zsel) with the gains of the
+// last backward pass, summed in knot order: the gradient statistic of an inner iteration whose line
+// search failed, i.e. with Z_ unchanged (ilqr.hpp:571-575).  One lane, serial.
+template <class LaneT>
+__device__ __forceinline__ double gain_sum_serial(const LaneT& L, int zsel) {
+  constexpr int n = LaneT::n, m = LaneT::m;
+  const int N = L.P.N, W = L.P.W;
+  double gs = 0.0;
+  for (int k = 0; k < N; ++k) gs += knot_gain<m>(L.kd(k) + m * n * W, W, L.z(zsel, k) + n * W, W);
+  return gs;
+}
+// The same sum formed by the G lanes that share an instance (the warp holds WI = 32/G instances):
+// they take the knots round-robin into the instance's gbuf[N] (shared), lane a = 0 adds them up
+// in knot order (same additions as the serial version).  Warp-collective; `want` per instance.
+template <class LaneT>
+__device__ __forceinline__ double gain_sum_warp(const LaneT& L, bool want, int zsel, double* gbuf) {
+  constexpr int n = LaneT::n, m = LaneT::m, G = LaneT::G;
+  const int N = L.P.N, W = L.P.W;
+  if (want)
+    for (int k = L.a; k < N; k += G) gbuf[k] = knot_gain<m>(L.kd(k) + m * n * W, W, L.z(zsel, k) + n * W, W);
+  __syncwarp();
+  double gs = 0.0;
+  if (want && L.a == 0)
+    for (int k = 0; k < N; ++k) gs += gbuf[k];
+  __syncwarp();
+  return gs;
+}
+
 // Acceptance over the G candidates of every instance of the warp (tries done0 + a), given each
 // candidate's cost J and rollout outcome; same rules and tie-breaking as p_line_search.
 template <int WI>
@@ -524,7 +569,7 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_roll_wide(SolverParams P) {
                 static_cast<size_t>(warp) * p_roll_stage_doubles<M>(W);
   const int b = tile * W + lane % W;
   const LaneT L(P, smem, b, lane / W, lane % W, b < P.B);
-  const bool run = L.valid && L.is(I_PHASE) == kPhInner && L.is(I_LSFAIL) == 0;
+  const bool run = L.valid && L.is(I_PHASE) == kPhInner;
   if (!__any_sync(kFull, run)) return;
   const int zsel = run ? L.is(I_ZSEL) : 0;
   int st_try = run ? L.is(I_STATUS) : kUnsolved;
@@ -553,7 +598,7 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_cost_wide(SolverParams P) {
     const int b = tile * W + i;
     if (b >= P.B) continue;
     const PLane<M, W, W> L(P, s_blob, b, a, i, true);
-    if (L.is(I_PHASE) != kPhInner || L.is(I_LSFAIL) != 0 || a >= P.opt.line_search_max_iterations) continue;
+    if (L.is(I_PHASE) != kPhInner || a >= P.opt.line_search_max_iterations) continue;
     const int zsel = L.is(I_ZSEL);
     const double* zc = L.z((zsel + 1 + a) % (G + 1), k);
     double x[n], u[m];
@@ -579,7 +624,7 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_acc_wide(SolverParams P, in
   double* gbuf = reinterpret_cast<double*>(smem) + static_cast<size_t>(warp) * W * N;
   const int b = tile * W + lane % W;
   const LaneT L(P, nullptr, b, lane / W, lane % W, b < P.B);
-  const bool run = L.valid && L.is(I_PHASE) == kPhInner && L.is(I_LSFAIL) == 0;
+  const bool run = L.valid && L.is(I_PHASE) == kPhInner;
   if (!__any_sync(kFull, run)) return;
   int zsel = 0, st = kUnsolved, st_try = kUnsolved;
   double J0 = 0.0, dV0 = 0.0, dV1 = 0.0, csrc = -1.0;
@@ -618,7 +663,8 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_acc_wide(SolverParams P, in
   }
   if (run && L.a == 0) {
     if (r.success || r.exhausted) {
-      p_finish(L, mode, r, (zsel + 1 + r.slot) % (G + 1), zsel, J0, csrc, st);
+      p_finish(L, mode, r, (zsel + 1 + r.slot) % (G + 1), zsel, J0, csrc, st,
+               r.success ? 0.0 : gain_sum_serial(L, zsel));
     } else {  // continue with try G in the deep kernels
       L.sc(S_CSRC_ALPHA) = csrc;
       L.is(I_STATUS) = st;
@@ -725,7 +771,9 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_acc_deep(SolverParams P, in
       r.gsum = gs;
     }
   }
-  if (lane == 0) p_finish(L, mode, r, new_zsel, zsel, J0, csrc, st);
+  double gs_bwd = 0.0;
+  if (!r.success) gs_bwd = gain_sum_warp(L, true, zsel, gbuf);
+  if (lane == 0) p_finish(L, mode, r, new_zsel, zsel, J0, csrc, st, gs_bwd);
 }
 
 // First G = 32/W tries of every instance in kPhInner whose previous search did not fail
@@ -743,7 +791,7 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_ls_wide(SolverParams P, int
                 static_cast<size_t>(warp) * p_stage_doubles<M>(P.pmax, W);
   const int b = tile * W + lane % W;
   const LaneT L(P, smem, b, lane / W, lane % W, b < P.B);
-  const bool run = L.valid && L.is(I_PHASE) == kPhInner && L.is(I_LSFAIL) == 0;
+  const bool run = L.valid && L.is(I_PHASE) == kPhInner;
   if (!__any_sync(kFull, run)) return;
   int zsel = 0, st = kUnsolved;
   double penalty = 1.0, J0 = 0.0, dV0 = 0.0, dV1 = 0.0, csrc = -1.0;
@@ -760,7 +808,8 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_ls_wide(SolverParams P, int
   const PLsResult r = p_line_search<M, W, W>(L, stg, run, zsel, zo, W, nz * W, penalty, J0, dV0, dV1, st, csrc, 0, 1);
   if (run && L.a == 0) {
     if (r.success || r.exhausted) {
-      p_finish(L, mode, r, (zsel + 1 + r.slot) % (G + 1), zsel, J0, csrc, st);
+      p_finish(L, mode, r, (zsel + 1 + r.slot) % (G + 1), zsel, J0, csrc, st,
+               r.success ? 0.0 : gain_sum_serial(L, zsel));
     } else {  // continue with try G in k_ls_deep
       L.sc(S_CSRC_ALPHA) = csrc;
       L.is(I_STATUS) = st;
@@ -771,42 +820,54 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_ls_wide(SolverParams P, int
 
 // The remaining tries of the instances on P.list, one instance per warp, 32 tries per round.
 // entry = (instance << 1) | from_wide: from_wide = 1 -> the first `wide_tries` tries are done.
-// Candidates go to the warp's scratch block of P.CAND; the accepted one is copied into the
-// instance's next trajectory buffer by the whole warp.
+// The search only needs each candidate's cost: nothing is stored while searching (most entries are
+// instances whose search fails at every step length).  The accepted candidate, if any, is rolled
+// out once more by its lane straight into the instance's next trajectory buffer, which also yields
+// its normalised feed-forward gain — the same arithmetic on the same inputs, hence the same
+// trajectory the search evaluated.
 #ifndef ALTRO_DEEP_MINB
 #define ALTRO_DEEP_MINB 4
 #endif
-template <class M, int W>
+template <class M>
+__host__ __device__ constexpr int p_deep_warp_doubles(int pmax, int N, int WI) {
+  return p_stage_doubles<M>(pmax, WI) + WI * N;
+}
+// WI instances per warp, G = 32/WI tries each per round: WI = 2 when the tries left after the wide
+// kernel fit 16 lanes (the default 20 - 4), WI = 1 otherwise.
+template <class M, int W, int WI>
 __global__ void __launch_bounds__(kLsWarps* kWarp, ALTRO_DEEP_MINB) k_ls_deep(SolverParams P, int mode, int wide_tries) {
   extern __shared__ __align__(128) char smem[];
   const int count = P.counters[3];
-  if (static_cast<int>(blockIdx.x) * kLsWarps >= count) return;
+  if (static_cast<int>(blockIdx.x) * kLsWarps * WI >= count) return;
   copy_blob(P.blob, smem, P.blob_bytes);
   const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
-  const int j = blockIdx.x * kLsWarps + warp;
-  if (j >= count) return;
-  using LaneT = PLane<M, W, 1>;
+  const int j0 = (blockIdx.x * kLsWarps + warp) * WI;
+  if (j0 >= count) return;
+  using LaneT = PLane<M, W, WI>;
   constexpr int nz = LaneT::nz, GZ = kWarp / W;  // GZ + 1 trajectory buffers exist per instance
   double* stg = reinterpret_cast<double*>(smem + ((P.blob_bytes + 15) / 16) * 16) +
-                static_cast<size_t>(warp) * p_stage_doubles<M>(P.pmax, 1);
-  const int entry = P.list[j];
-  const LaneT L(P, smem, entry >> 1, lane, 0, true);
+                static_cast<size_t>(warp) * p_deep_warp_doubles<M>(P.pmax, P.N, WI);
+  const int si = lane % WI, a = lane / WI;
+  const bool valid = j0 + si < count;
+  const int entry = P.list[valid ? j0 + si : j0];
+  const LaneT L(P, smem, entry >> 1, a, si, valid);
+  double* gbuf = stg + p_stage_doubles<M>(P.pmax, WI) + si * P.N;
   const int done0 = (entry & 1) ? wide_tries : 0;
   int zsel = L.is(I_ZSEL), st = L.is(I_STATUS);
   const double penalty = L.sc(S_PENALTY), J0 = L.sc(S_J0), dV0 = L.sc(S_DV0), dV1 = L.sc(S_DV1);
   double csrc = L.sc(S_CSRC_ALPHA);
-  double* cand = P.CAND + static_cast<size_t>(j) * (P.N + 1) * nz * kWarp;
-  const PLsResult r = p_line_search<M, W, 1>(L, stg, true, zsel, cand + lane, kWarp, nz * kWarp, penalty, J0, dV0,
-                                             dV1, st, csrc, done0, 1 << 30);
+  PLsResult r = p_line_search<M, W, WI, false>(L, stg, valid, zsel, nullptr, 0, 0, penalty, J0, dV0, dV1, st, csrc,
+                                               done0, 1 << 30);
   const int new_zsel = (zsel + 1) % (GZ + 1);
-  __syncwarp();
-  if (r.success) {
-    const double* src = cand + r.slot;
-    double* dst = L.z(new_zsel, 0);
-    const int total = (P.N + 1) * nz;
-    for (int e = lane; e < total; e += kWarp) dst[static_cast<size_t>(e) * W] = src[static_cast<size_t>(e) * kWarp];
+  const bool succ = valid && r.success;
+  if (__any_sync(kFull, succ)) {
+    double J2, gs;
+    int st2 = kUnsolved;
+    p_rollout<M, W, WI>(L, stg, succ && a == r.slot, zsel, L.z(new_zsel, 0), W, nz * W, r.alpha, penalty, J2, gs, st2);
+    r.gsum = __shfl_sync(kFull, gs, si + WI * (succ ? r.slot : 0));
   }
-  if (lane == 0) p_finish(L, mode, r, new_zsel, zsel, J0, csrc, st);
+  const double gs_bwd = gain_sum_warp(L, valid && !r.success, zsel, gbuf);
+  if (valid && a == 0) p_finish(L, mode, r, new_zsel, zsel, J0, csrc, st, gs_bwd);
 }
 
 // ------------------------------------------------------------------------------------------

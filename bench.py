@@ -116,7 +116,7 @@ def profiled_traffic():
     import glob
     import re
     best = None
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_backward_mat_summary.txt"))):
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_backward_mat_phased_summary.txt"))):
         txt = open(path).read()
         rd = re.search(r"dram__bytes_read\.sum \[Mbyte\] = ([0-9.]+)", txt)
         wr = re.search(r"dram__bytes_write\.sum \[Mbyte\] = ([0-9.]+)", txt)
@@ -146,7 +146,8 @@ def cpu_model() -> str:
 
 
 def cpu_leg(spec, X0, steps, warmup, sample, nthreads):
-    """Times the CPU oracle (port of the reference algorithm) on a bounded sample."""
+    """Times the CPU oracle (port of the reference algorithm) on a bounded sample (this process: the
+    parity build, -O3 -ffp-contract=off)."""
     from oracle import binding as ob
     ob.build()
     Xs = X0[:sample]
@@ -159,6 +160,33 @@ def cpu_leg(spec, X0, steps, warmup, sample, nthreads):
         if i >= warmup:
             times.append(dt)
     return sample / float(np.mean(times)), float(np.mean(times)), out
+
+
+CPU_BUILD = "g++ -O3 -march=native (oracle/Makefile liboracle_native.so, built on this host)"
+
+
+def cpu_leg_native(workload_name, batch, steps, warmup, sample, nthreads):
+    """The timed CPU arm: the same port compiled as BASELINE.md section 3 says (-O3 -march=native), run in
+    a child process so that the parity build stays the checker of this one.
+    -> (solves/s, seconds per step, {"status", "iters"} of the sample)."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        out_npz = os.path.join(tmp, "cpu.npz")
+        env = dict(os.environ, ALTRO_ORACLE_VARIANT="native")
+        cmd = [sys.executable, os.path.abspath(__file__), "--cpu-child", out_npz, "--workload", workload_name,
+               "--batch", str(batch), "--cpu-sample", str(sample), "--steps", str(steps), "--warmup", str(warmup),
+               "--cpu-threads", str(nthreads)]
+        subprocess.run(cmd, env=env, check=True, stdout=subprocess.DEVNULL)
+        d = np.load(out_npz)
+        dt = float(d["dt"])
+        return sample / dt, dt, {"status": d["status"], "iters": d["iters"]}
+
+
+def cpu_child(args):
+    spec, gen_x0, default_B, _ = workload(args.workload)
+    X0 = gen_x0(spec, args.batch or default_B)
+    _, dt, out = cpu_leg(spec, X0, args.steps, args.warmup, args.cpu_sample, args.cpu_threads)
+    np.savez(args.cpu_child, dt=dt, status=out["status"], iters=out["iters"])
 
 
 def main():
@@ -175,7 +203,11 @@ def main():
     ap.add_argument("--engine", default=None, choices=["phased", "fused"],
                     help="execution engine (default: the library's, phased); results are identical")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--cpu-child", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-threads", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_child:
+        return cpu_child(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,15 +223,17 @@ def main():
         X0 = gen_x0(spec, B)
         sample = min(args.cpu_sample, B)
         W = max(0, args.warmup)
-        val, dt, out = cpu_leg(spec, X0, args.steps, W, sample, ncores)
+        val, dt, out = cpu_leg_native(args.workload, B, args.steps, W, sample, ncores)
         line = {
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "batch_per_step": sample,
                        "note": "CPU path of the reference algorithm (oracle port; the reference cannot be "
-                               "built here: Eigen absent), one independent solve per host thread"},
+                               "built here: Eigen absent), one independent solve per host thread",
+                       "build": CPU_BUILD},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "cpu_model": cpu_model(),
+                             "build": CPU_BUILD,
                              "sample": f"first {sample} instances of the {B}-instance batch per step"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
@@ -289,27 +323,37 @@ def main():
     h2d = B * n * 8
     d2h = B * ((N + 1) * n + N * m) * 8 + B * (8 + 8 + 4 + 12)
 
-    # ---- roofline: the materialised backward-pass kernel, timed live
+    # ---- roofline: the backward-pass kernel, timed live.  `roofline` is the variant a solve launches
+    # (k_backward_mat<..., phased>: per-instance phase mask + regularisation hand-off) at the full batch;
+    # the bare streaming variant (writes K, d only, no solve state) is reported beside it.
     ms_bp = float('nan')
+    ms_bp_stream = float('nan')
     bp_bytes = solver.backward_pass_bytes()
+
+    def time_bp(fn):
+        for _ in range(3):
+            fn(stream=stream)
+        barrier()
+        ea = torch.cuda.Event(enable_timing=True)
+        eb = torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        for _ in range(args.bp_iters):
+            fn(stream=stream)
+        eb.record(stream)
+        barrier()
+        return ea.elapsed_time(eb) / args.bp_iters
+
     with torch.cuda.stream(stream):
       if not args.workload.startswith('c5'):
         solver.set_inputs_dev(x0_dev.data_ptr(), 0, unom, stream=stream)
         solver.solve_setup(stream=stream)
         solver.rollout(stream=stream)
         solver.update_expansions(stream=stream)
-        for _ in range(3):
-            solver.backward_pass_stream_only(stream=stream)
-        barrier()
-        e4 = torch.cuda.Event(enable_timing=True)
-        e5 = torch.cuda.Event(enable_timing=True)
-        e4.record(stream)
-        for _ in range(args.bp_iters):
-            solver.backward_pass_stream_only(stream=stream)
-        e5.record(stream)
-        barrier()
-        ms_bp = e4.elapsed_time(e5) / args.bp_iters
-    bp_bytes = solver.backward_pass_bytes()
+        ms_bp_stream = time_bp(solver.backward_pass_stream_only)
+        if solver.engine == "phased":
+            ms_bp = time_bp(solver.backward_pass_insolve)
+        else:
+            ms_bp = ms_bp_stream
     peak, peak_src = measured_peak()
     have_bp = ms_bp == ms_bp
     achieved = bp_bytes / (ms_bp * 1e-3) / 1e9 if have_bp else None
@@ -341,12 +385,18 @@ def main():
         res2 = solver2.results()
         X2, U2 = solver2.trajectory()
         X1, U1 = X_sol, U_sol
-        identical = bool(np.array_equal(res2["cost"], res["cost"]) and np.array_equal(res2["iters"], res["iters"])
-                         and np.array_equal(res2["status"], res["status"]) and np.array_equal(X1, X2)
-                         and np.array_equal(U1, U2))
+        # raw-bit comparison per field (NaN-safe: an instance that diverged to NaN on both sides is equal)
+        bits = lambda a: np.ascontiguousarray(a).view(np.int64) if a.dtype == np.float64 else a
+        fields = {"cost": (res["cost"], res2["cost"]), "viol": (res["viol"], res2["viol"]),
+                  "iters": (res["iters"], res2["iters"]), "status": (res["status"], res2["status"]),
+                  "X": (X1, X2), "U": (U1, U2)}
+        mismatch = {k: int((bits(a) != bits(b)).reshape(B, -1).any(axis=1).sum()) for k, (a, b) in fields.items()}
+        identical = not any(mismatch.values())
         extras = {"skip_repeated_iterations": {
             "ms_per_step_rank0": ms_skip, "value_rank0": B / (ms_skip * 1e-3), "unit": UNIT,
             "bit_identical_to_faithful_run": identical,
+            "instances_differing_per_field": mismatch,
+            "nan_instances": int(np.isnan(X1).reshape(B, -1).any(axis=1).sum()),
             "note": "opt-in option, off in the headline: inner iterations that provably repeat the previous "
                     "one (same Z, duals, penalty and regularisation after a fully failed line search) are "
                     "counted, not executed"}}
@@ -370,15 +420,19 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu:
         sample = min(args.cpu_sample, B)
-        val, dt, out = cpu_leg(spec, X0_host, 1, 0, sample, ncores)
-        same = float(np.mean(np.all(out["iters"] == res["iters"][:sample], axis=1)
-                             & (out["status"] == res["status"][:sample])))
+        # timed arm: the -march=native build in a child process; checker: the parity build here
+        val, dt, out_native = cpu_leg_native(args.workload, B, 1, 0, sample, ncores)
+        _, _, out = cpu_leg(spec, X0_host, 1, 0, sample, ncores)
+        agree = lambda o: float(np.mean(np.all(o["iters"] == res["iters"][:sample], axis=1)
+                                        & (o["status"] == res["status"][:sample])))
         n1 = min(48, sample)
-        val1, dt1, _ = cpu_leg(spec, X0_host, 1, 0, n1, 1)
+        val1, dt1, _ = cpu_leg_native(args.workload, B, 1, 0, n1, 1)
         cpu = {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "cpu_model": cpu_model(),
+               "build": CPU_BUILD,
                "sample": f"first {sample} instances of rank 0's batch, one pass ({dt:.1f} s)",
                "single_thread_value": val1, "single_thread_sample": f"first {n1} instances ({dt1:.1f} s)",
-               "same_status_and_iterations_as_gpu": same}
+               "same_status_and_iterations_as_gpu": agree(out),
+               "same_status_and_iterations_as_gpu_native_build": agree(out_native)}
 
     if rank == 0:
         line = {
@@ -397,15 +451,21 @@ def main():
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": None if not have_bp else {"kernel": "k_backward_mat (materialised backward pass, TMA-streamed)",
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src,
-                         "traffic": (profiled_traffic() or (None, None))[0] if args.workload == "c2" and B == 16384 else None,
-                         "traffic_source": (profiled_traffic() or (None, None))[1],
-                         "bytes_per_launch": bp_bytes, "ms_per_launch": ms_bp},
+            "roofline": None if not have_bp else {
+                "kernel": "k_backward_mat<phased> — the backward pass as a solve launches it (TMA-streamed "
+                          "materialised expansions), full batch",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": (profiled_traffic() or (None, None))[0] if args.workload == "c2" and B == 16384 else None,
+                "traffic_source": (profiled_traffic() or (None, None))[1],
+                "bytes_per_launch": bp_bytes, "ms_per_launch": ms_bp,
+                "stream_only_variant": {"ms_per_launch": ms_bp_stream,
+                                        "achieved": bp_bytes / (ms_bp_stream * 1e-3) / 1e9,
+                                        "frac": bp_bytes / (ms_bp_stream * 1e-3) / 1e9 / peak}},
             "solve_engine": {"engine": solver.engine,
-                             "kernels": ("k_solve(outer/start) || k_update_expansions -> k_backward_mat(TMA) -> "
-                                         "k_ls_wide/k_ls_deep (k_roll/k_cost/k_acc when few instances remain)")
+                             "kernels": ("k_outer_* (dense list, every 2nd slot) -> k_update_expansions -> "
+                                         "k_backward_mat(TMA) -> k_ls_wide -> k_ls_deep (k_roll/k_cost/k_acc when few "
+                                         "instances remain)")
                              if solver.engine == "phased" else "k_solve (fused persistent AL-iLQR)",
                              "backward_passes_per_step": float(stats[1].item()),
                              "contract_GBps": float(stats[1].item()) * (bp_bytes / B) / (ms * 1e-3) / 1e9},

@@ -209,6 +209,10 @@ int altro_b200_solve_setup(altro_b200_solver* s, void* stream);
  *   _fused       : UpdateExpansions fused into the backward sweep (what the solve kernel runs). */
 int altro_b200_backward_pass_stream_only(altro_b200_solver* s, void* stream);
 int altro_b200_backward_pass_fused(altro_b200_solver* s, void* stream);
+/* the backward-pass kernel as a whole solve launches it (per-instance phase mask, regularisation
+ * hand-off), every instance marked active; needs update_expansions first and scrambles the solve
+ * state — measurement only (bench.py roofline) */
+int altro_b200_backward_pass_insolve(altro_b200_solver* s, void* stream);
 
 /* --- outputs (any pointer may be NULL) -----------------------------------------------
  * GetTrajectory() (ilqr.hpp:140) -> X [B][N+1][n], U [B][N][m] */

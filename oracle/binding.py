@@ -13,7 +13,11 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+# ALTRO_ORACLE_VARIANT=native selects the -O3 -march=native build (bench.py's timed CPU arm runs in a
+# subprocess with it set); the default is the parity build every check uses.
+_NATIVE = os.environ.get("ALTRO_ORACLE_VARIANT", "") == "native"
+_LIB_NAME = "liboracle_native.so" if _NATIVE else "liboracle.so"
+_LIB_PATH = os.path.join(_HERE, _LIB_NAME)
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
 
@@ -22,9 +26,31 @@ def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in ("altro_oracle_capi.cpp", "altro_oracle.hpp", "altro_oracle.h")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
-    if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    if force or stale or (_NATIVE and not _native_built_here()):
+        subprocess.check_call(["make", "-C", _HERE, "-B", _LIB_NAME], stdout=subprocess.DEVNULL)
+        if _NATIVE:
+            with open(_LIB_PATH + ".host", "w") as f:
+                f.write(_host_id())
     return _LIB_PATH
+
+
+def _host_id() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                import hashlib
+                return hashlib.sha1(line.encode()).hexdigest()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def _native_built_here() -> bool:
+    """-march=native objects are only valid on the CPU they were built on."""
+    try:
+        return open(_LIB_PATH + ".host").read() == _host_id()
+    except Exception:
+        return False
 
 
 class Options(ctypes.Structure):

@@ -1,0 +1,98 @@
+"""Reproducibility of the CUDA path at BASELINE.json's batch sizes (reference analogue: the re-solve
+determinism check of test/augmented_lagrangian/auglag_test.cpp:353-380 and the nthreads-equivalence
+tests of test/ilqr/ilqr_class_test.cpp:130-160).
+
+Two FRESH solvers (other device addresses, no history) on identical inputs, driven like bench.py
+drives them — device-resident inputs on a non-blocking stream — must agree bit for bit on every
+output: status, iteration counters, cost, violation, X, U, K, d.  So must a solver with the opt-in
+stall skip.  Compared as raw bits (NaN-safe).
+"""
+import numpy as np
+import pytest
+
+from altro_cpp_b200 import problems as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (the product path has no CPU fallback)")
+    import altro_cpp_b200 as pkg
+    pkg.set_default_engine(None)
+    return pkg
+
+
+def _bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.int64) if a.dtype == np.float64 else a
+
+
+def _solve_like_bench(gpu, spec, X0, options=None, solves=2):
+    import torch
+    B = X0.shape[0]
+    dev = torch.device("cuda", 0)
+    x0_dev = torch.from_numpy(X0).to(dev)
+    stream = torch.cuda.Stream(device=dev)  # non-blocking, like bench.py
+    s = gpu.BatchSolver(spec, B, options=options)
+    with torch.cuda.stream(stream):
+        for _ in range(solves):
+            s.set_inputs_dev(x0_dev.data_ptr(), 0, spec.u0, stream=stream)
+            s.solve_al(stream=stream)
+        torch.cuda.synchronize(dev)
+    r = s.results()
+    X, U = s.trajectory()
+    K, d = s.gains()
+    return dict(status=r["status"], iters=r["iters"], cost=r["cost"], viol=r["viol"], X=X, U=U, K=K, d=d)
+
+
+def _assert_identical(a, b, B, what):
+    bad = {k: int((_bits(a[k]) != _bits(b[k])).reshape(B, -1).any(axis=1).sum()) for k in a}
+    assert not any(bad.values()), f"{what}: instances differing per field {bad}"
+
+
+@pytest.mark.parametrize("case", ["c2", "c3", "c4"])
+def test_fresh_solvers_are_bit_identical_at_baseline_batch(gpu, case):
+    if case == "c2":
+        spec, scale, B = P.unicycle_problem(P.K_THREE_OBSTACLES), P.UNICYCLE_X0_SCALE, 16384
+    elif case == "c3":
+        spec, scale, B = P.triple_integrator_problem(dof=2, N=50, add_constraints=True), P.TRIPLE_INTEGRATOR_X0_SCALE, 8192
+    else:
+        spec, scale, B = P.cartpole_problem(N=200), P.CARTPOLE_X0_SCALE, 32768
+    X0 = P.perturbed_initial_states(spec, B, scale)
+    a = _solve_like_bench(gpu, spec, X0, solves=1)   # first solve of a fresh solver: lazily allocated scratch
+    b = _solve_like_bench(gpu, spec, X0, solves=3)   # third solve of another one
+    _assert_identical(a, b, B, "two fresh solvers")
+    o = gpu.default_options()
+    o.skip_repeated_iterations = 1
+    c = _solve_like_bench(gpu, spec, X0, options=o, solves=1)
+    _assert_identical(a, c, B, "skip_repeated_iterations")
+
+
+def test_backward_pass_after_solve_needs_update_expansions(gpu):
+    """The records left in EXP by a whole solve are per-slot scratch, not the expansion of Z_:
+    BackwardPass must ask for UpdateExpansions instead of running on them (and must not touch
+    cost-to-go arrays that were never allocated)."""
+    spec = P.unicycle_problem(P.K_TURN90)
+    X0 = P.perturbed_initial_states(spec, 16, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, 16, use_constraints=False)
+    s.set_inputs(X0)
+    s.solve_ilqr()
+    with pytest.raises(gpu.SolverError, match="UpdateExpansions"):
+        s.backward_pass()
+    s.update_expansions()
+    s.backward_pass()
+    P0, p0 = s.ctg(0)
+    assert np.all(np.isfinite(P0)) and np.all(np.isfinite(p0))
+
+
+def test_dense_and_diagonal_cost_paths_agree_bitwise(gpu, monkeypatch):
+    """The diagonal-cost fast path drops exact-zero products only: same bits as the dense path."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    X0 = P.perturbed_initial_states(spec, 96, P.UNICYCLE_X0_SCALE)
+    a = _solve_like_bench(gpu, spec, X0, solves=1)
+    monkeypatch.setenv("ALTRO_B200_DENSE_COST", "1")
+    b = _solve_like_bench(gpu, spec, X0, solves=1)
+    _assert_identical(a, b, 96, "dense vs diagonal cost evaluation")

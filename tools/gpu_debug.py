@@ -99,6 +99,14 @@ if __name__ == "__main__":
         X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
         o = pkg.default_options(); o.max_iterations_inner = 3; o.max_iterations_outer = 1
         s = pkg.BatchSolver(spec, B, options=o); s.set_inputs(X0); s.solve_al(); torch.cuda.synchronize()
+    if what == "ncu_bp_insolve":
+        spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+        B = 16384
+        X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+        s = pkg.BatchSolver(spec, B); s.set_inputs(X0)
+        s.solve_setup(); s.rollout(); s.update_expansions()
+        for _ in range(6): s.backward_pass_insolve()
+        torch.cuda.synchronize()
     if what == "ncu_bp":
         spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
         B = 16384

@@ -25,10 +25,10 @@ print(f"total {tot/1e3:.2f} ms over {len(rows)} launches")
 for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"  {t/1e3:9.3f} ms {100*t/tot:5.1f}%  x{c:5d}  avg {t/c:8.1f} us  {name}")
 if len(sys.argv) > 2:
-    # per-slot table for the phased engine: a slot starts at each k_solve launch
+    # per-slot table for the phased engine: a slot starts at each k_update_expansions launch
     slots = []
     for _, name, grid, t in rows:
-        if name.startswith("k_solve"):
+        if name.startswith("k_update_expansions"):
             slots.append(collections.OrderedDict())
         if slots:
             key = name.split("<")[0]
