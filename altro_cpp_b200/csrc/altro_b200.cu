@@ -315,10 +315,11 @@ Ops make_ops() {
       const long items = static_cast<long>(P.B) * nk;
       const int item_grid = static_cast<int>(std::min<long>((items + kOuterThreads - 1) / kOuterThreads, sm_count * 16));
       k_outer_select<<<(P.B + 255) / 256, 256, 0, st>>>(P);
-      k_outer_rollout<M, W, true><<<lane_grid, kOuterThreads, 0, st>>>(P);
+      const int force = std::getenv("ALTRO_B200_ALWAYS_ROLLOUT") ? 1 : 0;
+      k_outer_rollout<M, W, true><<<lane_grid, kOuterThreads, 0, st>>>(P, force);
       k_outer_duals<M, W><<<item_grid, kOuterThreads, 0, st>>>(P);
       k_outer_decide<<<lane_grid, kOuterThreads, 0, st>>>(P);
-      k_outer_rollout<M, W, false><<<lane_grid, kOuterThreads, 0, st>>>(P);
+      k_outer_rollout<M, W, false><<<lane_grid, kOuterThreads, 0, st>>>(P, force);
       k_outer_cost<M, W><<<item_grid, kOuterThreads, 0, st>>>(P);
       k_outer_finish<<<lane_grid, kOuterThreads, 0, st>>>(P, mode);
       *nlaunch = 7;
@@ -434,6 +435,12 @@ int choose_tile_width(int batch, int sm_count) {
 // ------------------------------------------------------------------------------------------
 // Solver
 // ------------------------------------------------------------------------------------------
+// ALTRO_B200_NO_FILL_SYNC=1 restores the round-1 behaviour (no synchronisation after the zero-fill of
+// lazily allocated scratch) — only to demonstrate the race it caused on non-blocking streams.
+static void sync_after_fill() {
+  if (!std::getenv("ALTRO_B200_NO_FILL_SYNC")) cudaDeviceSynchronize();
+}
+
 static int env_split_max() {
   const char* e = std::getenv("ALTRO_B200_SPLIT_MAX");
   return e ? std::atoi(e) : 2048;
@@ -486,7 +493,7 @@ struct altro_b200_solver {
     int rc = alloc(p, bytes);
     if (rc) return rc;
     cudaMemset(*p, 0, bytes);
-    cudaDeviceSynchronize();
+    sync_after_fill();
     return 0;
   }
   int ensure_io(size_t bytes) {
@@ -768,8 +775,8 @@ int altro_b200_problem_add_control_bound(altro_b200_problem* p, int k, const dou
   p->ineq[k].push_back(b);
   return 0;
 }
-int altro_b200_problem_add_circles(altro_b200_problem* p, int k, int nc, const double* cx, const double* cy,
-                                   const double* cr, int xi, int yi) {
+static int add_circles_impl(altro_b200_problem* p, int k, int nc, const double* cx, const double* cy,
+                            const double* cr, bool squared, int xi, int yi) {
   if (!p || !cx || !cy || !cr || k < 0 || k > p->N || nc <= 0 || nc > kMaxDim || xi < 0 || yi < 0 ||
       xi >= p->n || yi >= p->n)
     return fail(ALTRO_B200_ERR_ARG, "add_circles: bad argument");
@@ -783,10 +790,18 @@ int altro_b200_problem_add_circles(altro_b200_problem* p, int k, int nc, const d
   for (int i = 0; i < nc; ++i) {
     b.a[i] = cx[i];
     b.b[i] = cy[i];
-    b.c[i] = cr[i];
+    b.c[i] = squared ? cr[i] : cr[i] * cr[i];
   }
   p->ineq[k].push_back(b);
   return 0;
+}
+int altro_b200_problem_add_circles(altro_b200_problem* p, int k, int nc, const double* cx, const double* cy,
+                                   const double* cr, int xi, int yi) {
+  return add_circles_impl(p, k, nc, cx, cy, cr, false, xi, yi);
+}
+int altro_b200_problem_add_circles_r2(altro_b200_problem* p, int k, int nc, const double* cx, const double* cy,
+                                      const double* cr2, int xi, int yi) {
+  return add_circles_impl(p, k, nc, cx, cy, cr2, true, xi, yi);
 }
 int altro_b200_problem_set_initial_state(altro_b200_problem* p, const double* x0) {
   if (!p || !x0) return fail(ALTRO_B200_ERR_ARG, "set_initial_state: null argument");
@@ -989,7 +1004,7 @@ static int ensure_secondary(altro_b200_solver* s, int which) {
   cudaMemset(w.P.X0, fill, static_cast<size_t>(cap) * s->n * sizeof(double));
   cudaMemset(w.P.sc, 0, static_cast<size_t>(S_NUM) * cap * sizeof(double));
   cudaMemset(w.P.is, 0, static_cast<size_t>(I_NUM) * cap * sizeof(int));
-  cudaDeviceSynchronize();  // the legacy-stream memsets above are not ordered with a non-blocking user stream
+  sync_after_fill();  // the legacy-stream memsets above are not ordered with a non-blocking user stream
   w.allocated = true;
   return 0;
 }
@@ -1021,7 +1036,7 @@ static int ensure_secondary_buffers(altro_b200_solver* s, int which, int nbuf, i
   }
   // cudaMemset runs on the legacy default stream, which a non-blocking user stream does not wait
   // for: without this the memset could land AFTER the re-pack kernel queued next on the solve's stream
-  if (fresh) cudaDeviceSynchronize();
+  if (fresh) sync_after_fill();
   return 0;
 }
 

@@ -71,7 +71,8 @@ struct ConBlock {
   int idx[kMaxDim];   // control bound: control index of row i
   double a[kMaxDim];  // goal: xf | bound: bound value of row i | circle: cx
   double b[kMaxDim];  // circle: cy
-  double c[kMaxDim];  // circle: r
+  double c[kMaxDim];  // circle: r^2, rounded once on the host like the reference's pow(r, 2)
+                      // (obstacle_constraints.hpp:37 there)
 };
 
 // The constraints of one knot in ALCost order: equalities then inequalities
@@ -172,6 +173,8 @@ enum ScalarField : int {
   S_VTMP,          // phased engine scratch: bit pattern of a running max violation (atomicMax on the
                    // unsigned view of non-negative doubles: exact and order-independent)
   S_REG_IN, S_DREG_IN,  // regularisation at the entry of the current inner iteration (phased engine hand-off)
+  S_CAND_ALPHA,    // phased engine: step length of the rejected candidate that trajectory buffer zsel + 1 still
+                   // holds (the last try of a failed search), or < 0; saves regenerating it for Q8
   S_NUM
 };
 enum IntField : int {
@@ -182,6 +185,8 @@ enum IntField : int {
   I_PHASE,         // SolvePhase: where the instance is in its solve (k_solve is resumable)
   I_ORIG,          // index of the instance in the solver's primary workspace (compaction)
   I_LSFAIL,        // 1: the instance's last line search failed completely (scheduling hint only)
+  I_ROLLED,        // 1: the states of Z_ are the rollout of its controls from x0 (set when a solve has rolled it
+                   // out, cleared when inputs or states are set): phased engine skips re-rollouts that change nothing
   I_NUM
 };
 

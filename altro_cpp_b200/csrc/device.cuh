@@ -429,7 +429,7 @@ __device__ __forceinline__ double con_row_fast(const ConBlock& b, int i, const d
     }
     default: {
       const double dx = pick<n>(x, b.xi) - b.a[i], dy = pick<n>(x, b.yi) - b.b[i];
-      return -(dx * dx + dy * dy - b.c[i] * b.c[i]);
+      return -(dx * dx + dy * dy - b.c[i]);
     }
   }
 }
@@ -492,7 +492,7 @@ __device__ __forceinline__ void for_row_chunks(const BlockHdr& hd, const ConBloc
       ok[q] = q < p;
       ic[q] = ok[q] ? q : p - 1;
       const double dx = px - b.a[q], dy = py - b.b[q];  // rows past p: zero-filled, masked by f
-      c[q] = -(dx * dx + dy * dy - b.c[q] * b.c[q]);
+      c[q] = -(dx * dx + dy * dy - b.c[q]);
     }
     f(c, ic, ok);
   } else if (hd.kind == kCircle) {
@@ -506,7 +506,7 @@ __device__ __forceinline__ void for_row_chunks(const BlockHdr& hd, const ConBloc
         ok[q] = r0 + q < p;
         ic[q] = ok[q] ? r0 + q : p - 1;
         const double dx = px - b.a[ic[q]], dy = py - b.b[ic[q]];
-        c[q] = -(dx * dx + dy * dy - b.c[ic[q]] * b.c[ic[q]]);  // obstacle_constraints.hpp:107-110
+        c[q] = -(dx * dx + dy * dy - b.c[ic[q]]);  // obstacle_constraints.hpp:107-110
       }
       f(c, ic, ok);
     }

@@ -927,8 +927,8 @@ __global__ void k_move_instances(SolverParams src, SolverParams dst, const int* 
     const double* x = src.X0 + static_cast<size_t>(ts) * n * Ws + is_;
     double* xo = dst.X0 + static_cast<size_t>(td) * n * Wd + id;
     for (int q = 0; q < n; ++q) xo[q * Wd] = x[q * Ws];
-    for (int f = 0; f < S_NUM; ++f)
-      dst.sc[static_cast<size_t>(f) * dst.Bp + bd] = src.sc[static_cast<size_t>(f) * src.Bp + bs];
+    for (int f = 0; f < S_NUM; ++f)  // (the candidate buffers do not move with the instance)
+      dst.sc[static_cast<size_t>(f) * dst.Bp + bd] = (f == S_CAND_ALPHA) ? -1.0 : src.sc[static_cast<size_t>(f) * src.Bp + bs];
     for (int f = 0; f < I_NUM; ++f) {
       int v = src.is[static_cast<size_t>(f) * src.Bp + bs];
       if (f == I_ZSEL) v = 0;
@@ -1394,7 +1394,9 @@ __global__ void k_pack_inputs(SolverParams P, const double* __restrict__ x0,
     double* px0 = P.X0 + static_cast<size_t>(tile) * n * W + i;
     for (int q = 0; q < n; ++q) px0[q * W] = x0[static_cast<size_t>(src) * n + q];
     P.is[static_cast<size_t>(I_ZSEL) * P.Bp + b] = 0;
+    P.is[static_cast<size_t>(I_ROLLED) * P.Bp + b] = 0;
     P.sc[static_cast<size_t>(S_CSRC_ALPHA) * P.Bp + b] = -1.0;
+    P.sc[static_cast<size_t>(S_CAND_ALPHA) * P.Bp + b] = -1.0;
   }
 }
 
@@ -1407,6 +1409,7 @@ __global__ void k_set_states(SolverParams P, const double* __restrict__ X) {
   const int sel = P.is[static_cast<size_t>(I_ZSEL) * P.Bp + b];
   double* z = P.Z[sel] + (static_cast<size_t>(tile) * (N + 1) + k) * nz * W + i;
   for (int q = 0; q < n; ++q) z[q * W] = X[(static_cast<size_t>(b) * (N + 1) + k) * n + q];
+  if (k == 0) P.is[static_cast<size_t>(I_ROLLED) * P.Bp + b] = 0;
 }
 
 // generic gather: dst[b][kk][f] = src[tile][k0+kk][f0+f][i], f < nf.  sel_by_zsel: the source is

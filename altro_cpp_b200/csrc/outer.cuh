@@ -80,8 +80,14 @@ __global__ void __launch_bounds__(256) k_outer_select(SolverParams P) {
 // evaluated candidate; it is regenerated into candidate buffer (zsel + 1) so that the dual update
 // sees the same values (RolloutClosedLoop(alpha), ilqr.hpp:468-499).
 // (e) Rollout(), ilqr.hpp:453-459.
+// Both are skipped where they would only reproduce bits that are already there: the deep line search
+// leaves the last try of a failed search in buffer zsel + 1 (S_CAND_ALPHA says which step length it
+// holds); and Z_ of an instance that has been through an iLQR solve was produced by a rollout of
+// the same discrete dynamics from the same x0 and controls (I_ROLLED), so rolling it out again returns it
+// unchanged (tests: the fused engine, which always rolls out, is bit-identical).  force != 0 runs
+// them regardless (ALTRO_B200_ALWAYS_ROLLOUT=1).
 template <class M, int W, bool kClosed>
-__global__ void __launch_bounds__(kOuterThreads) k_outer_rollout(SolverParams P) {
+__global__ void __launch_bounds__(kOuterThreads) k_outer_rollout(SolverParams P, int force) {
   constexpr int n = M::n, m = M::m, nz = n + m, nkd = Inst<M, W>::nkd, GZ = kWarp / W;
   const int count = P.counters[4];
   const Desc D(P.blob);  // uniform descriptor words straight from global memory (L1-resident)
@@ -93,6 +99,7 @@ __global__ void __launch_bounds__(kOuterThreads) k_outer_rollout(SolverParams P)
     const int ph = I.is(I_PHASE);
     const double alpha = kClosed ? I.sc(S_CSRC_ALPHA) : 0.0;
     if (kClosed ? !(ph == kPhOuter && alpha >= 0.0) : ph != kPhSolveStart) continue;
+    if (!force && (kClosed ? I.sc(S_CAND_ALPHA) == alpha : I.is(I_ROLLED) != 0)) continue;
     const int zsel = I.is(I_ZSEL);
     const int zout = kClosed ? (zsel + 1) % (GZ + 1) : zsel;
     double x[n], u[m];
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(kOuterThreads) k_outer_finish(SolverParams P, 
       sc(S_J0) = J;
       sc(S_INITIAL_COST) = J;
       sc(S_CSRC_ALPHA) = -1.0;
+      is(I_ROLLED) = 1;
       is(I_PHASE) = (o.max_iterations_inner > 0) ? kPhInner : (mode == 1 ? kPhOuter : kPhDone);
     } else {  // Cost() of the final trajectory under the final duals / penalty
       if (mode == 0) sc(S_VIOL) = sc(S_VTMP);  // == GetMaxViolation() after Cost()

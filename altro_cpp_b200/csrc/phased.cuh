@@ -65,13 +65,13 @@ __host__ __device__ constexpr int p_stage_doubles(int pmax, int WI) {
 // Returns false when the state/control bound check trips (status is set like the reference).
 // kDbg (latency probe only, 0 in every solve kernel): 1 no cost, 2 no dynamics, 4 no staging
 // after knot 0, 8 no candidate stores, 16 no normalised-gain division
-// kStore = false: the candidate is evaluated but not written anywhere (the deep search only needs
+// store = false: the candidate is evaluated but not written anywhere (the deep search only needs
 // its cost; the winner is rolled out again to its destination).  kGain = false: no normalised
 // feed-forward gain (gsum = 0).
-template <class M, int W, int WI, int kDbg = 0, bool kStore = true, bool kGain = true>
+template <class M, int W, int WI, int kDbg = 0, bool kGain = true>
 __device__ __forceinline__ bool p_rollout(const PLane<M, W, WI>& L, double* stg, bool active, int zsel,
                                           double* zo, int zrow, int zknot, double alpha, double penalty,
-                                          double& J, double& gsum, int& status) {
+                                          double& J, double& gsum, int& status, bool store = true) {
   constexpr int n = M::n, m = M::m, nz = n + m, nkd = PLane<M, W, WI>::nkd;
   const int N = L.P.N, pmax = L.P.pmax;
   const DevOptions& o = L.P.opt;
@@ -163,7 +163,7 @@ __device__ __forceinline__ bool p_rollout(const PLane<M, W, WI>& L, double* stg,
         ALTRO_UNROLL
         for (int q = 0; q < m; ++q) u[q] = 0.0;
       }
-      if (kStore && !(kDbg & 8)) {
+      if (store && !(kDbg & 8)) {
         ALTRO_UNROLL
         for (int q = 0; q < n; ++q) zn[q * zrow] = x[q];
         ALTRO_UNROLL
@@ -216,6 +216,9 @@ struct PLsResult {
   double J, alpha, z, gsum;
 };
 
+// kStore = false (deep search): candidates are not written, except the LAST try allowed by
+// line_search_max_iterations, which goes to zo: if the whole search fails that is the candidate whose
+// constraint values the reference keeps (Q8), and the outer step finds it there.
 template <class M, int W, int WI, bool kStore = true>
 __device__ __forceinline__ PLsResult p_line_search(const PLane<M, W, WI>& L, double* stg, bool run, int zsel,
                                                    double* zo, int zrow, int zknot, double penalty,
@@ -241,8 +244,8 @@ __device__ __forceinline__ PLsResult p_line_search(const PLane<M, W, WI>& L, dou
     const bool mine = searching && (done + L.a < o.line_search_max_iterations);
     double J = 0.0, gs = 0.0, z = -1.0;
     int st_try = status;
-    const bool ok = p_rollout<M, W, WI, 0, kStore, kStore>(L, stg, mine, zsel, zo, zrow, zknot, alpha, penalty, J, gs,
-                                                           st_try);
+    const bool ok = p_rollout<M, W, WI, 0, kStore>(L, stg, mine, zsel, zo, zrow, zknot, alpha, penalty, J, gs, st_try,
+                                                   kStore || done + L.a == o.line_search_max_iterations - 1);
     bool acc = false;
     if (mine && ok) {
       const double expected = -alpha * (dV0 + alpha * dV1);
@@ -298,7 +301,7 @@ __device__ __forceinline__ PLsResult p_line_search(const PLane<M, W, WI>& L, dou
 // gsum_bwd: sum_k max_i |d_i|/(|u_i|+1) over the current Z_ (only read when the search failed).
 template <class LaneT>
 __device__ __forceinline__ void p_finish(const LaneT& L, int mode, const PLsResult& r, int new_zsel, int zsel,
-                                         double J0, double csrc, int st, double gsum_bwd) {
+                                         double J0, double csrc, int st, double gsum_bwd, double cand_alpha = -1.0) {
   const DevOptions& o = L.P.opt;
   double cost_cur = L.sc(S_COST_CUR), cost_prev = L.sc(S_COST_PREV);
   const double initial_cost = L.sc(S_INITIAL_COST);
@@ -325,6 +328,7 @@ __device__ __forceinline__ void p_finish(const LaneT& L, int mode, const PLsResu
   L.sc(S_ALPHA) = alpha_stat;
   L.sc(S_ZRATIO) = z_stat;
   L.sc(S_CSRC_ALPHA) = csrc;
+  L.sc(S_CAND_ALPHA) = r.success ? -1.0 : cand_alpha;
   L.sc(S_GRAD) = grad;
   L.sc(S_DJ) = dJ;
   L.sc(S_REG) = reg;
@@ -778,8 +782,11 @@ __global__ void __launch_bounds__(kLsWarps* kWarp) k_acc_deep(SolverParams P, in
 
 // First G = 32/W tries of every instance in kPhInner whose previous search did not fail
 // completely.  One warp per tile, lane = a*W + i.
+#ifndef ALTRO_WIDE_MINB
+#define ALTRO_WIDE_MINB 1
+#endif
 template <class M, int W>
-__global__ void __launch_bounds__(kLsWarps* kWarp) k_ls_wide(SolverParams P, int mode) {
+__global__ void __launch_bounds__(kLsWarps* kWarp, ALTRO_WIDE_MINB) k_ls_wide(SolverParams P, int mode) {
   extern __shared__ __align__(128) char smem[];
   copy_blob(P.blob, smem, P.blob_bytes);
   const int warp = threadIdx.x / kWarp, lane = threadIdx.x % kWarp;
@@ -856,9 +863,11 @@ __global__ void __launch_bounds__(kLsWarps* kWarp, ALTRO_DEEP_MINB) k_ls_deep(So
   int zsel = L.is(I_ZSEL), st = L.is(I_STATUS);
   const double penalty = L.sc(S_PENALTY), J0 = L.sc(S_J0), dV0 = L.sc(S_DV0), dV1 = L.sc(S_DV1);
   double csrc = L.sc(S_CSRC_ALPHA);
-  PLsResult r = p_line_search<M, W, WI, false>(L, stg, valid, zsel, nullptr, 0, 0, penalty, J0, dV0, dV1, st, csrc,
-                                               done0, 1 << 30);
   const int new_zsel = (zsel + 1) % (GZ + 1);
+  PLsResult r = p_line_search<M, W, WI, false>(L, stg, valid, zsel, L.z(new_zsel, 0), W, nz * W, penalty, J0, dV0, dV1,
+                                               st, csrc, done0, 1 << 30);
+  // the last try sits in buffer new_zsel; it is the Q8 candidate iff it was the last rollout that ran to the end
+  const double cand_alpha = (csrc == try_alpha(P.opt, P.opt.line_search_max_iterations - 1)) ? csrc : -1.0;
   const bool succ = valid && r.success;
   if (__any_sync(kFull, succ)) {
     double J2, gs;
@@ -867,7 +876,7 @@ __global__ void __launch_bounds__(kLsWarps* kWarp, ALTRO_DEEP_MINB) k_ls_deep(So
     r.gsum = __shfl_sync(kFull, gs, si + WI * (succ ? r.slot : 0));
   }
   const double gs_bwd = gain_sum_warp(L, valid && !r.success, zsel, gbuf);
-  if (valid && a == 0) p_finish(L, mode, r, new_zsel, zsel, J0, csrc, st, gs_bwd);
+  if (valid && a == 0) p_finish(L, mode, r, new_zsel, zsel, J0, csrc, st, gs_bwd, cand_alpha);
 }
 
 // ------------------------------------------------------------------------------------------

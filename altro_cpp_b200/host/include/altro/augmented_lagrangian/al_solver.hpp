@@ -1,0 +1,175 @@
+// altro/augmented_lagrangian/al_solver.hpp (B200 host mirror) — AugmentedLagrangianiLQR<n,m>
+// (reference: altro/augmented_lagrangian/al_solver.hpp:28-440) for one instance, and
+// BatchedAugmentedLagrangianiLQR<n,m>, the form the device is built for: B instances of one
+// problem that differ in initial state, solved by one set of kernel launches.
+//
+//   Solve()            al_solver.hpp:304   altro_b200_solve_al
+//   UpdateDuals()                 :336     altro_b200_update_duals
+//   UpdatePenalties()             :347     altro_b200_update_penalties
+//   SetPenalty(rho)               :271     altro_b200_solver_set_penalty
+//   MaxViolation()                :417     altro_b200_get_results_host (viol)
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <utility>
+#include <vector>
+
+#include "altro/augmented_lagrangian/al_cost.hpp"
+#include "altro/augmented_lagrangian/al_problem.hpp"
+#include "altro/ilqr/ilqr.hpp"
+
+namespace altro {
+namespace augmented_lagrangian {
+
+template <int n, int m>
+class AugmentedLagrangianiLQR {
+ public:
+  // AugmentedLagrangianiLQR(N) + InitializeFromProblem(prob), al_solver.hpp:35-38 there
+  explicit AugmentedLagrangianiLQR(int N) : ilqr_solver_(N) {}
+  explicit AugmentedLagrangianiLQR(const problem::Problem& prob, int device = 0)
+      : device_(device), ilqr_solver_(prob.NumSegments()) {
+    InitializeFromProblem(prob);
+  }
+  void InitializeFromProblem(const problem::Problem& prob) {
+    ALTRO_ASSERT(prob.IsFullyDefined(), "Expected problem to be fully defined.");
+    std::shared_ptr<Trajectory<n, m>> Z = ilqr_solver_.GetTrajectory();
+    core_ = std::make_shared<detail::DeviceSolver>(prob, prob.GetDynamics(0)->StateDimension(),
+                                                   prob.GetDynamics(0)->ControlDimension(), true, 1, device_);
+    ilqr_solver_ = ilqr::iLQR<n, m>(core_);
+    costs_.clear();
+    for (int k = 0; k <= prob.NumSegments(); ++k) costs_.emplace_back(std::make_shared<ALCost<n, m>>(core_, k));
+    if (Z) ilqr_solver_.SetTrajectory(Z);
+  }
+  std::shared_ptr<ALCost<n, m>> GetALCost(int k) { return costs_.at(k); }
+
+  void SetTrajectory(std::shared_ptr<Trajectory<n, m>> traj) { ilqr_solver_.SetTrajectory(std::move(traj)); }
+  ilqr::iLQR<n, m>& GetiLQRSolver() { return ilqr_solver_; }
+  SolverOptions& GetOptions() { return core_->GetOptions(); }
+  SolverStats& GetStats() { return core_->GetStats(); }
+  SolverStatus GetStatus() { return static_cast<SolverStatus>(core_->Pull().status[0]); }
+  int NumSegments() const { return core_->NumSegments(); }
+
+  void SetPenalty(double rho) { core_->SetPenalty(rho); }
+  void SetPenaltyScaling(double phi) { core_->SetPenaltyScaling(phi); }
+
+  void Solve() {
+    auto Z = ilqr_solver_.GetTrajectory();
+    if (!Z) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
+    core_->Upload(*Z);
+    core_->Run(detail::DeviceSolver::kSolveAL);
+    core_->Download(Z.get());
+    core_->Pull();
+    core_->PullHistory();
+  }
+  void UpdateDuals() { core_->Run(detail::DeviceSolver::kUpdateDuals); }
+  void UpdatePenalties() { core_->Run(detail::DeviceSolver::kUpdatePenalties); }
+  double MaxViolation() {
+    core_->Run(detail::DeviceSolver::kCost);
+    return core_->Pull().viol[0];
+  }
+  double GetMaxViolation() { return MaxViolation(); }
+  double GetMaxPenalty() { return core_->MaxPenalty(0); }
+  int NumConstraints(int k) const { return core_->GetProblem().NumConstraints(k); }
+  int NumConstraints() const { return core_->GetProblem().NumConstraints(); }
+  // dual variables of knot k, equalities then inequalities (GetALCost(k)->...->GetDuals() there)
+  VectorXd GetDuals(int k) {
+    const std::vector<double> lam = core_->Duals(k, 0);
+    VectorXd out = VectorXd::Zero(static_cast<int>(lam.size()));
+    for (int i = 0; i < out.size(); ++i) out(i) = lam[i];
+    return out;
+  }
+
+  // al_solver.hpp:85-104 there: one entry per constraint and knot point with its violation
+  // c - Pi_K(c) of the current trajectory, optionally sorted by its infinity norm
+  std::vector<constraints::ConstraintInfo> GetConstraintInfo(bool should_sort = false) {
+    const problem::Problem& prob = core_->GetProblem();
+    std::vector<constraints::ConstraintInfo> coninfo;
+    for (int k = 0; k <= NumSegments(); ++k) {
+      if (prob.NumConstraints(k) == 0) continue;
+      const std::vector<double> c = core_->ConstraintValues(k, 0);
+      int row = 0;
+      for (const auto& con : prob.GetEqualityConstraints()[k]) {
+        constraints::ConstraintInfo info{con->GetLabel(), k, VectorXd::Zero(con->OutputDimension()), con->GetConstraintType()};
+        for (int i = 0; i < info.violation.size(); ++i) info.violation(i) = c.at(row++);
+        coninfo.push_back(info);
+      }
+      for (const auto& con : prob.GetInequalityConstraints()[k]) {
+        constraints::ConstraintInfo info{con->GetLabel(), k, VectorXd::Zero(con->OutputDimension()), con->GetConstraintType()};
+        for (int i = 0; i < info.violation.size(); ++i) {
+          const double ci = c.at(row++);
+          info.violation(i) = ci > 0.0 ? ci : 0.0;
+        }
+        coninfo.push_back(info);
+      }
+    }
+    if (should_sort)
+      std::stable_sort(coninfo.begin(), coninfo.end(),
+                       [](const constraints::ConstraintInfo& a, const constraints::ConstraintInfo& b) {
+                         return InfNorm(a.violation) > InfNorm(b.violation);
+                       });
+    return coninfo;
+  }
+  void PrintViolations(bool should_sort = false, int precision = 4) {
+    const std::vector<constraints::ConstraintInfo> coninfo = GetConstraintInfo(should_sort);
+    std::printf("Got %d constraints\n", static_cast<int>(coninfo.size()));
+    for (const constraints::ConstraintInfo& info : coninfo) std::printf("%s\n", info.ToString(precision).c_str());
+  }
+
+ private:
+  static double InfNorm(const VectorXd& v) {
+    double r = 0.0;
+    for (int i = 0; i < v.size(); ++i) r = std::fabs(v(i)) > r ? std::fabs(v(i)) : r;
+    return r;
+  }
+  int device_ = 0;
+  std::shared_ptr<detail::DeviceSolver> core_;
+  ilqr::iLQR<n, m> ilqr_solver_;
+  std::vector<std::shared_ptr<ALCost<n, m>>> costs_;
+};
+
+// The batch axis replaces the reference's thread pool (SolverOptions::nthreads): instance b
+// starts from initial state x0[b] and the controls of the trajectory given to SetTrajectory.
+template <int n, int m>
+class BatchedAugmentedLagrangianiLQR {
+ public:
+  BatchedAugmentedLagrangianiLQR(const problem::Problem& prob, int batch, int device = 0)
+      : core_(std::make_shared<detail::DeviceSolver>(prob, prob.GetDynamics(0)->StateDimension(),
+                                                     prob.GetDynamics(0)->ControlDimension(), true, batch, device)) {}
+
+  int Batch() const { return core_->Batch(); }
+  SolverOptions& GetOptions() { return core_->GetOptions(); }
+  void SetPenalty(double rho) { core_->SetPenalty(rho); }
+  void SetInitialStates(const std::vector<VectorXd>& x0) { core_->SetInitialStates(x0); }
+  void SetTrajectory(std::shared_ptr<Trajectory<n, m>> nominal) {
+    Z_ = std::move(nominal);
+    core_->SetStep(Z_->GetStep(0));
+  }
+  void Solve() {
+    if (!Z_) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
+    core_->Upload(*Z_);
+    core_->Run(detail::DeviceSolver::kSolveAL);
+    core_->Fetch();
+    core_->Pull();
+  }
+  SolverStatus GetStatus(int b) const { return static_cast<SolverStatus>(core_->Last().status.at(b)); }
+  int GetIterations(int b) const { return core_->Last().iters.at(static_cast<size_t>(b) * 3 + 2); }
+  int GetOuterIterations(int b) const { return core_->Last().iters.at(static_cast<size_t>(b) * 3 + 1); }
+  double GetCost(int b) const { return core_->Last().cost.at(b); }
+  double GetMaxViolation(int b) const { return core_->Last().viol.at(b); }
+  Trajectory<n, m> GetTrajectory(int b) const {
+    Trajectory<n, m> Z = *Z_;
+    core_->CopyOut(&Z, b);
+    return Z;
+  }
+  int64_t KernelLaunches() const { return core_->KernelLaunches(); }
+
+ private:
+  std::shared_ptr<detail::DeviceSolver> core_;
+  std::shared_ptr<Trajectory<n, m>> Z_;
+};
+
+}  // namespace augmented_lagrangian
+}  // namespace altro

@@ -131,6 +131,10 @@ int altro_b200_problem_add_control_bound(altro_b200_problem* p, int k, const dou
  * examples/obstacle_constraints.hpp:69-126 */
 int altro_b200_problem_add_circles(altro_b200_problem* p, int k, int ncircles, const double* cx,
                                    const double* cy, const double* cr, int xi, int yi);
+/* the same with squared radii (what a CircleConstraint evaluates at a circle's centre): lets a caller
+ * that only sees the functor's virtual interface describe it without losing a bit */
+int altro_b200_problem_add_circles_r2(altro_b200_problem* p, int k, int ncircles, const double* cx,
+                                      const double* cy, const double* cr2, int xi, int yi);
 /* SetInitialState(x0): the nominal initial state, altro/problem/problem.hpp:195-202 */
 int altro_b200_problem_set_initial_state(altro_b200_problem* p, const double* x0);
 

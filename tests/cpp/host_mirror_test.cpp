@@ -1,4 +1,4 @@
-// Reference-style tests written against the host mirror (altro_cpp_b200/host): they read like
+// Reference-style tests written against the host mirror (altro_cpp_b200/host/include): they read like
 // test/ilqr/unicycle_ilqr_test.cpp, test/augmented_lagrangian/auglag_test.cpp and
 // test/examples/example_*_test.cpp of the reference and expect the same golden numbers, but every
 // solver method runs on the device.
@@ -26,15 +26,81 @@ int failures = 0;
   } while (0)
 
 using altro::SolverStatus;
-using altro::problems::TripleIntegratorProblem;
+using TripleIntegratorProblem = altro::problems::TripleIntegratorProblem<2>;
 using altro::problems::UnicycleProblem;
 
-// a user-defined model without a device descriptor: the reference would call its virtual
+using altro::MatrixXd;
+using altro::VectorXd;
+using altro::VectorXdRef;
+
+// a user-defined model that is not in the device registry: the reference would call its virtual
 // Evaluate on the host; here the solver must refuse it
 class HostOnlyModel : public altro::problem::ContinuousDynamics {
  public:
+  static constexpr int NStates = 3;
+  static constexpr int NControls = 2;
   int StateDimension() const override { return 3; }
   int ControlDimension() const override { return 2; }
+  bool HasHessian() const override { return false; }
+  void Evaluate(const VectorXdRef& x, const VectorXdRef& u, float, Eigen::Ref<VectorXd> xdot) override {
+    xdot(0) = u(0) * x(1);
+    xdot(1) = -x(0);
+    xdot(2) = u(1);
+  }
+  void Jacobian(const VectorXdRef&, const VectorXdRef&, float, Eigen::Ref<MatrixXd> jac) override { jac.setZero(); }
+  void Hessian(const VectorXdRef&, const VectorXdRef&, float, const VectorXdRef&, Eigen::Ref<MatrixXd> hess) override {
+    hess.setZero();
+  }
+};
+
+// Functors that only have the reference's virtual interface (no Describable, no accessors), like the
+// classes of an unmodified altro-cpp checkout: the registry must recognise them by probing.
+class PlainCircles : public altro::constraints::Constraint<altro::constraints::Inequality> {
+ public:
+  int OutputDimension() const override { return 2; }
+  void Evaluate(const VectorXdRef& x, const VectorXdRef&, Eigen::Ref<VectorXd> c) override {
+    c(0) = -(std::pow(x(1) - 0.75, 2) + std::pow(x(0) - 0.5, 2) - std::pow(0.425, 2));  // position = states (1, 0)
+    c(1) = -(std::pow(x(1) - 2.25, 2) + std::pow(x(0) + 1.0, 2) - std::pow(0.3, 2));
+  }
+  void Jacobian(const VectorXdRef& x, const VectorXdRef&, Eigen::Ref<MatrixXd> jac) override {
+    jac(0, 0) = 2 * (0.75 - x(1));
+    jac(0, 1) = 2 * (0.5 - x(0));
+    jac(1, 0) = 2 * (2.25 - x(1));
+    jac(1, 1) = 2 * (-1.0 - x(0));
+  }
+};
+class PlainBound : public altro::constraints::Constraint<altro::constraints::Inequality> {
+ public:
+  int OutputDimension() const override { return 3; }  // lb_0, ub_0, ub_1 finite
+  void Evaluate(const VectorXdRef&, const VectorXdRef& u, Eigen::Ref<VectorXd> c) override {
+    c(0) = -0.25 - u(0);
+    c(1) = u(0) - 3.0;
+    c(2) = u(1) - 1.5;
+  }
+  void Jacobian(const VectorXdRef&, const VectorXdRef&, Eigen::Ref<MatrixXd> jac) override {
+    jac.setZero();
+    jac(0, 3) = -1;
+    jac(1, 3) = 1;
+    jac(2, 4) = 1;
+  }
+};
+class PlainCubicCost : public altro::problem::CostFunction {  // not a quadratic form
+ public:
+  int StateDimension() const override { return 3; }
+  int ControlDimension() const override { return 2; }
+  double Evaluate(const VectorXdRef& x, const VectorXdRef&) override { return x(0) * x(0) * x(0); }
+  void Gradient(const VectorXdRef& x, const VectorXdRef&, Eigen::Ref<VectorXd> dx, Eigen::Ref<VectorXd> du) override {
+    dx.setZero();
+    du.setZero();
+    dx(0) = 3 * x(0) * x(0);
+  }
+  void Hessian(const VectorXdRef& x, const VectorXdRef&, Eigen::Ref<MatrixXd> dxdx, Eigen::Ref<MatrixXd> dxdu,
+               Eigen::Ref<MatrixXd> dudu) override {
+    dxdx.setZero();
+    dxdu.setZero();
+    dudu.setZero();
+    dxdx(0, 0) = 6 * x(0);
+  }
 };
 
 void TestDescriptors() {
@@ -48,12 +114,47 @@ void TestDescriptors() {
   EXPECT(prob.NumConstraints(100) == 3);  // goal
   EXPECT(def.GetTimeStep() == 5.0f / 100);
 
+  std::string why;
   altro::device::ConstraintDesc d;
-  EXPECT(prob.GetInequalityConstraints()[1][0]->Describe(&d));
-  EXPECT(d.kind == altro::device::ConstraintDesc::kCircle && d.a.size() == 3 && d.c[0] == 0.425);
+  EXPECT(altro::device::DescribeConstraint(*prob.GetInequalityConstraints()[1][0], 3, 2, &d, &why));
+  EXPECT(d.kind == altro::device::ConstraintDesc::kCircle && d.a.size() == 3 && d.c[0] == 0.425 * 0.425);
   altro::device::CostDesc c;
-  EXPECT(prob.GetCostFunction(100)->Describe(&c));
+  EXPECT(altro::device::DescribeCost(*prob.GetCostFunction(100), 3, 2, &c, &why));
   EXPECT(c.Q[0] == 10.0 && c.q[0] == -30.0 && c.R[0] == 0.0);
+
+  // recognition by probing: the same functors seen ONLY through their virtual interface give the same
+  // descriptions, bit for bit (what an unmodified altro-cpp checkout's example classes go through)
+  {
+    struct Veil : altro::constraints::Constraint<altro::constraints::Inequality> {  // hides Describable
+      std::shared_ptr<altro::constraints::Constraint<altro::constraints::Inequality>> in;
+      int OutputDimension() const override { return in->OutputDimension(); }
+      void Evaluate(const VectorXdRef& x, const VectorXdRef& u, Eigen::Ref<VectorXd> o) override { in->Evaluate(x, u, o); }
+      void Jacobian(const VectorXdRef& x, const VectorXdRef& u, Eigen::Ref<MatrixXd> j) override { in->Jacobian(x, u, j); }
+    };
+    Veil veiled;
+    veiled.in = prob.GetInequalityConstraints()[1][0];
+    altro::device::ConstraintDesc p;
+    EXPECT(altro::device::DescribeConstraint(veiled, 3, 2, &p, &why));
+    EXPECT(p.kind == d.kind && p.a == d.a && p.b == d.b && p.c == d.c && p.xi == 0 && p.yi == 1);
+    veiled.in = prob.GetInequalityConstraints()[1][1];  // the control bound
+    altro::device::ConstraintDesc pb, db;
+    EXPECT(altro::device::DescribeConstraint(*veiled.in, 3, 2, &db, &why));
+    EXPECT(altro::device::DescribeConstraint(veiled, 3, 2, &pb, &why));
+    EXPECT(pb.kind == altro::device::ConstraintDesc::kControlBound && pb.a == db.a && pb.b == db.b);
+
+    PlainCircles circles;
+    EXPECT(altro::device::DescribeConstraint(circles, 3, 2, &p, &why));
+    EXPECT(p.kind == altro::device::ConstraintDesc::kCircle && p.xi == 1 && p.yi == 0);
+    EXPECT(p.a[0] == 0.75 && p.b[0] == 0.5 && p.c[0] == std::pow(0.425, 2) && p.a[1] == 2.25 && p.b[1] == -1.0);
+    PlainBound bound;
+    EXPECT(altro::device::DescribeConstraint(bound, 3, 2, &p, &why));
+    EXPECT(p.kind == altro::device::ConstraintDesc::kControlBound && p.a[0] == -0.25 && std::isinf(p.a[1]) &&
+           p.b[0] == 3.0 && p.b[1] == 1.5);
+    PlainCubicCost cubic;
+    altro::device::CostDesc pc;
+    EXPECT(!altro::device::DescribeCost(cubic, 3, 2, &pc, &why));
+    EXPECT(why.find("not a quadratic form") != std::string::npos);
+  }
 
   // ControlBound drops infinite rows (basic_constraints.hpp:136-143 there)
   altro::examples::ControlBound half(2);
@@ -118,7 +219,7 @@ void TestUnicycleILQR() {
   auto step = def.MakeSolver();
   step.UpdateExpansions();
   step.BackwardPass();
-  auto kpf = step.GetKnotPointFunction(0, true);
+  auto& kpf = step.GetKnotPointFunction(0);
   const double p0[3] = {0.024904637422419617, -0.46496022574032614, -0.0573096310550007};
   const double d0[2] = {-2.565783457444465, 5.514158930898376};
   for (int i = 0; i < 3; ++i) EXPECT(std::fabs(kpf.GetCostToGoGradient()(i) - p0[i]) < 1e-5 * 0.47);
@@ -126,7 +227,7 @@ void TestUnicycleILQR() {
   EXPECT(kpf.GetDynamicsExpansion().GetA().rows() == 3 && kpf.GetDynamicsExpansion().GetB().cols() == 2);
   EXPECT(kpf.GetDynamicsExpansion().GetA()(0, 0) == 1.0);  // d x_next / d x = 1 for the unicycle
   EXPECT(kpf.GetCostExpansion().dudu()(0, 0) > 0.0);
-  EXPECT(step.NumThreads() == 1 && step.GetTaskAssignment().back() == def.N + 1);
+  EXPECT(step.NumThreads() == 0 && step.GetTaskAssignment().back() == def.N + 1);  // no pool for one thread
 
   // the problem's initial state is shared with the solver (ilqr_class_test.cpp:84-96)
   {
@@ -150,7 +251,7 @@ void TestUnicycleILQR() {
   EXPECT(std::fabs(fresh.Cost() - 0.0387016567) < 1e-5);
   const altro::VectorXd& xN = fresh.GetTrajectory()->State(def.N);
   EXPECT(std::fabs(xN(0) - 1.5) < 1e-2 && std::fabs(xN(1) - 1.5) < 1e-2);
-  auto g = fresh.GetKnotPointFunction(0);
+  auto& g = fresh.GetKnotPointFunction(0);
   EXPECT(g.GetFeedbackGain().rows() == 2 && g.GetFeedbackGain().cols() == 3);
 }
 

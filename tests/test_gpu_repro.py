@@ -96,3 +96,4 @@ def test_dense_and_diagonal_cost_paths_agree_bitwise(gpu, monkeypatch):
     monkeypatch.setenv("ALTRO_B200_DENSE_COST", "1")
     b = _solve_like_bench(gpu, spec, X0, solves=1)
     _assert_identical(a, b, 96, "dense vs diagonal cost evaluation")
+

@@ -1,4 +1,4 @@
-"""The host mirror of the reference's C++ API (altro_cpp_b200/host): reference-style programs
+"""The host mirror of the reference's C++ API (altro_cpp_b200/host/include): reference-style programs
 compile against it, refuse to run without a GPU and reproduce the reference's golden numbers on
 one (tests/cpp/host_mirror_test.cpp)."""
 import os
@@ -11,14 +11,15 @@ import altro_cpp_b200 as pkg
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "altro_cpp_b200")
-HOST = os.path.join(LIBDIR, "host")
+HOST = os.path.join(LIBDIR, "host", "include")          # altro/ + the Eigen stand-in: the library proper
+EXAMPLES = os.path.join(LIBDIR, "host", "examples_b200")  # this repo's own examples/ and perf/ programs
 
 
 def compile_program(tmp_path, src, name):
     pkg.lib()  # makes sure libaltro_b200.so exists
     exe = str(tmp_path / name)
     subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
-                           "-I", os.path.join(ROOT, "include"), "-I", HOST, src, "-o", exe,
+                           "-I", os.path.join(ROOT, "include"), "-I", HOST, "-I", EXAMPLES, src, "-o", exe,
                            "-L", LIBDIR, "-laltro_b200", f"-Wl,-rpath,{LIBDIR}"])
     return exe
 
@@ -41,7 +42,7 @@ def test_benchmark_programs_refuse_to_run_without_gpu(tmp_path):
     if has_gpu():
         pytest.skip("a GPU is present")
     for name in ("benchmark_unicycle", "benchmark_triple_integrator"):
-        exe = compile_program(tmp_path, os.path.join(HOST, "perf", name + ".cpp"), name)
+        exe = compile_program(tmp_path, os.path.join(EXAMPLES, "perf", name + ".cpp"), name)
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode == 2
         assert "no usable CUDA device" in r.stderr
@@ -64,7 +65,7 @@ def test_cmake_project_with_reference_target_names(tmp_path):
         f"set(ALTRO_B200_PREBUILT ON CACHE BOOL \"\")\nset(ALTRO_BUILD_TESTS OFF CACHE BOOL \"\")\n"
         f"set(ALTRO_BUILD_BENCHMARKS OFF CACHE BOOL \"\")\n"
         f"add_subdirectory({ROOT} altro)\nadd_executable(app app.cpp)\n"
-        "target_link_libraries(app PRIVATE altro::altro)\n")
+        "target_link_libraries(app PRIVATE altro::altro altro::example_problems)\n")
     (down / "app.cpp").write_text(
         '#include "altro/augmented_lagrangian/al_solver.hpp"\n#include "examples/problems/unicycle.hpp"\n'
         "int main() { altro::problems::UnicycleProblem p; return p.MakeProblem().NumSegments() == 100 ? 0 : 1; }\n")
@@ -83,7 +84,7 @@ def test_host_mirror_reproduces_reference_goldens_on_device(tmp_path):
 
 @pytest.mark.gpu
 def test_benchmark_unicycle_single_and_batched(tmp_path):
-    exe = compile_program(tmp_path, os.path.join(HOST, "perf", "benchmark_unicycle.cpp"), "benchmark_unicycle")
+    exe = compile_program(tmp_path, os.path.join(EXAMPLES, "perf", "benchmark_unicycle.cpp"), "benchmark_unicycle")
     r = subprocess.run([exe, "2"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("iters = 50, outer = 5, status = 0") == 2
