@@ -65,6 +65,10 @@ def lib():
         L.altro_b200_set_default_engine.argtypes = [ctypes.c_int]
         L.altro_b200_set_default_engine.restype = None
         L.altro_b200_solver_engine.argtypes = [_vp]
+        L.altro_b200_multi_create.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                              ctypes.c_int, ctypes.POINTER(_vp)]
+        L.altro_b200_multi_destroy.argtypes = [_vp]
+        L.altro_b200_multi_num_devices.argtypes = [_vp]
         _lib = L
     return _lib
 
@@ -299,3 +303,66 @@ class BatchSolver:
     def backward_pass_bytes(self) -> int: return int(lib().altro_b200_backward_pass_bytes(self._h))
     def kernel_launches(self) -> int: return int(lib().altro_b200_kernel_launches(self._h))
     def device_bytes(self) -> int: return int(lib().altro_b200_device_bytes(self._h))
+
+
+class MultiBatchSolver:
+    """The same batch sharded over several GPUs of one node behind ONE handle (altro_b200_multi_*):
+    contiguous slices, one solver and one host thread per device, no collective.
+    `devices` may name a device more than once (two slices on one GPU: how the 1-GPU tests exercise it)."""
+
+    def __init__(self, spec: ProblemSpec, batch: int, devices, use_constraints: bool = True,
+                 options: Optional[Options] = None):
+        self.spec, self.B = spec, int(batch)
+        self.n, self.m, self.N = spec.n, spec.m, spec.N
+        self.devices = [int(d) for d in devices]
+        L = lib()
+        self._prob = spec.build(L, "altro_b200_")
+        h = _vp()
+        devs = (ctypes.c_int * len(self.devices))(*self.devices)
+        rc = L.altro_b200_multi_create(self._prob, self.B, int(use_constraints), devs, len(self.devices), ctypes.byref(h))
+        if rc != 0:
+            msg = L.altro_b200_last_error().decode()
+            L.altro_b200_problem_destroy(self._prob)
+            self._prob = None
+            raise SolverError(f"multi_create failed ({rc}): {msg}")
+        self._h = h
+        if options is not None:
+            _check(L.altro_b200_multi_set_options(self._h, ctypes.byref(options)), "multi_set_options")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                lib().altro_b200_multi_destroy(self._h)
+                self._h = None
+            if getattr(self, "_prob", None):
+                lib().altro_b200_problem_destroy(self._prob)
+                self._prob = None
+        except Exception:
+            pass
+
+    def solve_al_host(self, X0, U0=None, want_traj=True, out=None):
+        X0 = _f64(X0, (self.B, self.n))
+        unom, U = None, None
+        if U0 is None:
+            unom = _f64(self.spec.u0 if self.spec.u0 is not None else np.zeros(self.m))
+        else:
+            U = np.ascontiguousarray(np.broadcast_to(_f64(U0), (self.B, self.N, self.m)))
+        if out is None:
+            out = dict(cost=np.zeros(self.B), viol=np.zeros(self.B), status=np.zeros(self.B, np.int32),
+                       iters=np.zeros((self.B, 3), np.int32))
+            if want_traj:
+                out["X"] = np.zeros((self.B, self.N + 1, self.n))
+                out["U"] = np.zeros((self.B, self.N, self.m))
+        nul = ctypes.cast(None, _dp)
+        rc = lib().altro_b200_multi_solve_al_host(
+            self._h, _p(X0), _p(U), _p(unom), _p(out["X"]) if want_traj else nul, _p(out["U"]) if want_traj else nul,
+            _p(out["cost"]), _p(out["viol"]), out["status"].ctypes.data_as(_ip), out["iters"].ctypes.data_as(_ip))
+        _check(rc, "multi_solve_al_host")
+        return out
+
+    def timings(self):
+        """Device ms of the last solve per device: inputs H2D + packing, solve, results D2H."""
+        G = len(self.devices)
+        a, b, c = np.zeros(G), np.zeros(G), np.zeros(G)
+        _check(lib().altro_b200_multi_last_timings(self._h, _p(a), _p(b), _p(c)), "multi_last_timings")
+        return dict(scatter_ms=a, solve_ms=b, gather_ms=c)

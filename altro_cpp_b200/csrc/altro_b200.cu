@@ -1469,6 +1469,132 @@ int altro_b200_get_scalars_host(altro_b200_solver* s, double* reg, double* dV0, 
   return 0;
 }
 
+// ---------------------------------------------------------------- batch sharded over several GPUs
+// Instances are independent: contiguous slices of the batch go to one solver per
+// device; a host thread per device drives its slice (H2D of its inputs, the solve, D2H of its
+// results) on its own stream, so the devices work concurrently.  No collective anywhere.
+}  // extern "C"
+
+#include <thread>
+
+struct altro_b200_multi {
+  int n = 0, m = 0, N = 0, B = 0;
+  std::vector<int> devices, lo, hi;
+  std::vector<altro_b200_solver*> parts;
+  std::vector<cudaStream_t> streams;
+  std::vector<double> t_scatter, t_solve, t_gather;  // ms of the last solve, per device
+};
+
+extern "C" {
+
+int altro_b200_multi_create(const altro_b200_problem* p, int batch, int use_constraints, const int* devices,
+                            int ndev, altro_b200_multi** out) {
+  if (!p || !out || !devices || ndev <= 0 || batch < ndev)
+    return fail(ALTRO_B200_ERR_ARG, "multi_create: bad argument (need at least one instance per device)");
+  std::unique_ptr<altro_b200_multi, void (*)(altro_b200_multi*)> mm(new altro_b200_multi(), altro_b200_multi_destroy);
+  mm->n = p->n; mm->m = p->m; mm->N = p->N; mm->B = batch;
+  const int base = batch / ndev, rem = batch % ndev;
+  int lo = 0;
+  for (int g = 0; g < ndev; ++g) {  // contiguous slices, sizes differing by at most one
+    const int hi = lo + base + (g < rem ? 1 : 0);
+    mm->devices.push_back(devices[g]);
+    mm->lo.push_back(lo);
+    mm->hi.push_back(hi);
+    lo = hi;
+  }
+  mm->parts.assign(ndev, nullptr);
+  mm->streams.assign(ndev, nullptr);
+  mm->t_scatter.assign(ndev, 0.0);
+  mm->t_solve.assign(ndev, 0.0);
+  mm->t_gather.assign(ndev, 0.0);
+  for (int g = 0; g < ndev; ++g) {
+    int rc = altro_b200_solver_create(p, mm->hi[g] - mm->lo[g], use_constraints, devices[g], &mm->parts[g]);
+    if (rc) return rc;
+    DeviceGuard guard(devices[g]);
+    CU(cudaStreamCreateWithFlags(&mm->streams[g], cudaStreamNonBlocking));
+  }
+  *out = mm.release();
+  return 0;
+}
+
+void altro_b200_multi_destroy(altro_b200_multi* mm) {
+  if (!mm) return;
+  for (size_t g = 0; g < mm->parts.size(); ++g) {
+    if (mm->streams[g]) {
+      DeviceGuard guard(mm->devices[g]);
+      cudaStreamDestroy(mm->streams[g]);
+    }
+    altro_b200_solver_destroy(mm->parts[g]);
+  }
+  delete mm;
+}
+
+int altro_b200_multi_num_devices(const altro_b200_multi* mm) { return mm ? static_cast<int>(mm->parts.size()) : 0; }
+
+int altro_b200_multi_set_options(altro_b200_multi* mm, const altro_b200_options* o) {
+  if (!mm || !o) return fail(ALTRO_B200_ERR_ARG, "multi_set_options: null argument");
+  for (altro_b200_solver* s : mm->parts) {
+    int rc = altro_b200_solver_set_options(s, o);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int altro_b200_multi_solve_al_host(altro_b200_multi* mm, const double* x0, const double* U0, const double* u_nominal,
+                                   double* X, double* U, double* cost, double* viol, int32_t* status, int32_t* iters) {
+  if (!mm || !x0) return fail(ALTRO_B200_ERR_ARG, "multi_solve_al_host: null argument");
+  const int G = static_cast<int>(mm->parts.size());
+  const size_t n = mm->n, m = mm->m, N = mm->N;
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  auto work = [&](int g) {
+    cudaSetDevice(mm->devices[g]);
+    altro_b200_solver* s = mm->parts[g];
+    cudaStream_t st = mm->streams[g];
+    const size_t lo = mm->lo[g];
+    cudaEvent_t e[4];
+    for (cudaEvent_t& ev : e) cudaEventCreate(&ev);
+    int rc = 0;
+    cudaEventRecord(e[0], st);
+    rc = altro_b200_solver_set_inputs_host(s, x0 + lo * n, U0 ? U0 + lo * N * m : nullptr, u_nominal, st);
+    cudaEventRecord(e[1], st);
+    if (!rc) rc = altro_b200_solve_al(s, st);
+    cudaEventRecord(e[2], st);
+    if (!rc && (X || U)) rc = altro_b200_get_trajectory_host(s, X ? X + lo * (N + 1) * n : nullptr, U ? U + lo * N * m : nullptr, st);
+    if (!rc) rc = altro_b200_get_results_host(s, cost ? cost + lo : nullptr, viol ? viol + lo : nullptr,
+                                              status ? status + lo : nullptr, iters ? iters + lo * 3 : nullptr, st);
+    cudaEventRecord(e[3], st);
+    cudaStreamSynchronize(st);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e[0], e[1]); mm->t_scatter[g] = ms;
+    cudaEventElapsedTime(&ms, e[1], e[2]); mm->t_solve[g] = ms;
+    cudaEventElapsedTime(&ms, e[2], e[3]); mm->t_gather[g] = ms;
+    for (cudaEvent_t& ev : e) cudaEventDestroy(ev);
+    rcs[g] = rc;
+    if (rc) errs[g] = altro_b200_last_error();  // thread-local: carried back to the caller's thread
+  };
+  std::vector<std::thread> threads;
+  for (int g = 1; g < G; ++g) threads.emplace_back(work, g);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  work(0);
+  if (prev >= 0) cudaSetDevice(prev);
+  for (std::thread& t : threads) t.join();
+  for (int g = 0; g < G; ++g)
+    if (rcs[g]) return fail(rcs[g], "device " + std::to_string(mm->devices[g]) + ": " + errs[g]);
+  return 0;
+}
+
+int altro_b200_multi_last_timings(const altro_b200_multi* mm, double* scatter_ms, double* solve_ms, double* gather_ms) {
+  if (!mm) return fail(ALTRO_B200_ERR_ARG, "null handle");
+  for (size_t g = 0; g < mm->parts.size(); ++g) {
+    if (scatter_ms) scatter_ms[g] = mm->t_scatter[g];
+    if (solve_ms) solve_ms[g] = mm->t_solve[g];
+    if (gather_ms) gather_ms[g] = mm->t_gather[g];
+  }
+  return 0;
+}
+
 size_t altro_b200_backward_pass_bytes(const altro_b200_solver* s) {
   if (!s) return 0;
   const size_t n = s->n, m = s->m, N = s->N;

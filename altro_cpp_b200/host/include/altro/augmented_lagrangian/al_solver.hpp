@@ -138,6 +138,12 @@ class BatchedAugmentedLagrangianiLQR {
   BatchedAugmentedLagrangianiLQR(const problem::Problem& prob, int batch, int device = 0)
       : core_(std::make_shared<detail::DeviceSolver>(prob, prob.GetDynamics(0)->StateDimension(),
                                                      prob.GetDynamics(0)->ControlDimension(), true, batch, device)) {}
+  // the batch cut into contiguous slices over several GPUs of the node (one solver and one host thread
+  // per device, no collective; what SolverOptions::nthreads is to the reference, one level up)
+  BatchedAugmentedLagrangianiLQR(const problem::Problem& prob, int batch, const std::vector<int>& devices)
+      : core_(std::make_shared<detail::DeviceSolver>(prob, prob.GetDynamics(0)->StateDimension(),
+                                                     prob.GetDynamics(0)->ControlDimension(), true, batch,
+                                                     devices.empty() ? 0 : devices[0], devices)) {}
 
   int Batch() const { return core_->Batch(); }
   SolverOptions& GetOptions() { return core_->GetOptions(); }

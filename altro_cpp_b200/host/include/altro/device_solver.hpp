@@ -35,9 +35,11 @@ inline void Check(int rc, const char* what) {
 
 class DeviceSolver {
  public:
-  DeviceSolver(const problem::Problem& prob, int n, int m, bool use_constraints, int batch = 1, int device = 0)
+  // devices: more than one entry shards the batch over those GPUs (altro_b200_multi_*): whole solves only
+  DeviceSolver(const problem::Problem& prob, int n, int m, bool use_constraints, int batch = 1, int device = 0,
+               std::vector<int> devices = {})
       : prob_(prob), n_(n), m_(m), N_(prob.NumSegments()), B_(batch), device_(device),
-        use_constraints_(use_constraints) {
+        use_constraints_(use_constraints), devices_(std::move(devices)) {
     if (!prob_.IsFullyDefined()) throw std::invalid_argument("Expected problem to be fully defined.");
     if (batch < 1) throw std::invalid_argument("batch must be positive");
     X_.assign(static_cast<size_t>(B_) * (N_ + 1) * n_, 0.0);
@@ -46,7 +48,9 @@ class DeviceSolver {
   }
   ~DeviceSolver() {
     if (solver_) altro_b200_solver_destroy(solver_);
+    if (multi_) altro_b200_multi_destroy(multi_);
   }
+  bool Sharded() const { return devices_.size() > 1; }
   DeviceSolver(const DeviceSolver&) = delete;
   DeviceSolver& operator=(const DeviceSolver&) = delete;
 
@@ -64,6 +68,10 @@ class DeviceSolver {
     if (solver_ && h != h_) {
       altro_b200_solver_destroy(solver_);
       solver_ = nullptr;
+    }
+    if (multi_ && h != h_) {
+      altro_b200_multi_destroy(multi_);
+      multi_ = nullptr;
     }
     h_ = h;
     have_step_ = true;
@@ -107,6 +115,7 @@ class DeviceSolver {
       for (int k = 0; k < N_; ++k)
         for (int j = 0; j < m_; ++j) Ub[k * m_ + j] = Z.Control(k)(j);
     }
+    if (Sharded()) return;  // the sharded solve takes the host arrays directly
     Check(altro_b200_solver_set_inputs_host(solver_, x0_.data(), U_.data(), nullptr, nullptr), "SetTrajectory");
     Check(altro_b200_solver_set_states_host(solver_, X_.data(), nullptr), "SetTrajectory");
   }
@@ -117,6 +126,7 @@ class DeviceSolver {
     CopyOut(Z, b);
   }
   void Fetch() {
+    if (Sharded()) return;  // results arrived with the solve
     Need();
     Check(altro_b200_get_trajectory_host(solver_, X_.data(), U_.data(), nullptr), "GetTrajectory");
   }
@@ -145,6 +155,21 @@ class DeviceSolver {
     kSolveAL
   };
   void Run(Phase ph) {
+    if (Sharded()) {
+      if (ph != kSolveAL) throw DeviceError(ALTRO_B200_ERR_UNSUPPORTED, "a batch sharded over several GPUs supports whole solves only");
+      if (!multi_) throw DeviceError(ALTRO_B200_ERR_STATE, "SetTrajectory must be called before this method");
+      altro_b200_options d = MakeOptions();
+      Check(altro_b200_multi_set_options(multi_, &d), "GetOptions");
+      res_.cost.resize(B_);
+      res_.viol.resize(B_);
+      res_.status.resize(B_);
+      res_.iters.resize(static_cast<size_t>(B_) * 3);
+      std::vector<double> U0 = U_;  // U_ is overwritten with the solution
+      Check(altro_b200_multi_solve_al_host(multi_, x0_.data(), U0.data(), nullptr, X_.data(), U_.data(), res_.cost.data(),
+                                           res_.viol.data(), res_.status.data(), res_.iters.data()),
+            "Solve");
+      return;
+    }
     Need();
     PushOptions();
     int rc = ALTRO_B200_ERR_ARG;
@@ -171,6 +196,7 @@ class DeviceSolver {
     std::vector<double> initial_cost, reg;
   };
   const Results& Pull() {
+    if (Sharded()) return res_;
     Need();
     res_.cost.resize(B_);
     res_.viol.resize(B_);
@@ -300,6 +326,10 @@ class DeviceSolver {
     if (!solver_) throw DeviceError(ALTRO_B200_ERR_STATE, "SetTrajectory must be called before this method");
   }
   void PushOptions() {
+    altro_b200_options d = MakeOptions();
+    Check(altro_b200_solver_set_options(solver_, &d), "GetOptions");
+  }
+  altro_b200_options MakeOptions() {
     const SolverOptions& o = stats_.GetOptions();
     altro_b200_options d;
     altro_b200_default_options(&d);
@@ -325,12 +355,12 @@ class DeviceSolver {
     d.maximum_penalty = o.maximum_penalty;
     d.initial_penalty = o.initial_penalty;
     if (penalty_scaling_ > 0) d.penalty_scaling = penalty_scaling_;
-    Check(altro_b200_solver_set_options(solver_, &d), "GetOptions");
+    return d;
   }
 
   // Problem -> altro_b200_problem -> altro_b200_solver
   void Ensure() {
-    if (solver_) return;
+    if (solver_ || multi_) return;
     if (!have_step_) throw DeviceError(ALTRO_B200_ERR_STATE, "the trajectory carries no time step");
     altro_b200_problem* p = nullptr;
     Check(altro_b200_problem_create(n_, m_, N_, &p), "Problem");
@@ -368,6 +398,11 @@ class DeviceSolver {
       }
     }
     Check(altro_b200_problem_set_initial_state(p, prob_.GetInitialState().data()), "SetInitialState");
+    if (Sharded()) {
+      Check(altro_b200_multi_create(p, B_, use_constraints_ ? 1 : 0, devices_.data(), static_cast<int>(devices_.size()), &multi_),
+            "solver");
+      return;
+    }
     Check(altro_b200_solver_create(p, B_, use_constraints_ ? 1 : 0, device_, &solver_), "solver");
     if (have_penalty_) Check(altro_b200_solver_set_penalty(solver_, penalty_, nullptr), "SetPenalty");
   }
@@ -398,6 +433,8 @@ class DeviceSolver {
   int n_, m_, N_, B_, device_;
   bool use_constraints_;
   altro_b200_solver* solver_ = nullptr;
+  std::vector<int> devices_;
+  altro_b200_multi* multi_ = nullptr;
   float h_ = 0.0f;
   bool have_step_ = false;
   double penalty_ = 0.0;

@@ -21,6 +21,13 @@ class DiscretizedModelBase {
   virtual bool IsRungeKutta4() const = 0;
 };
 
+// RungeKutta4 with any compile-time sizes (the reference instantiates it with the model's sizes or with
+// the problem's, examples/problems/triple_integrator.hpp:43 there)
+template <class T>
+struct IsRk4 : std::false_type {};
+template <int NStates, int NControls>
+struct IsRk4<RungeKutta4<NStates, NControls>> : std::true_type {};
+
 template <class Model, class Integrator = RungeKutta4<Model::NStates, Model::NControls>>
 class DiscretizedModel : public DiscreteDynamics, public DiscretizedModelBase {
  public:
@@ -56,9 +63,7 @@ class DiscretizedModel : public DiscreteDynamics, public DiscretizedModelBase {
   Integrator& GetIntegrator() { return integrator_; }
 
   std::shared_ptr<ContinuousDynamics> GetContinuousModel() const override { return model_; }
-  bool IsRungeKutta4() const override {
-    return std::is_same<Integrator, RungeKutta4<Model::NStates, Model::NControls>>::value;
-  }
+  bool IsRungeKutta4() const override { return IsRk4<Integrator>::value; }
 
  private:
   std::shared_ptr<Model> model_;

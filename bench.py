@@ -189,6 +189,98 @@ def cpu_child(args):
     np.savez(args.cpu_child, dt=dt, status=out["status"], iters=out["iters"])
 
 
+def strong_scaling_c3(pkg, torch, dist, world, rank, dev, local_rank, stream, steps):
+    """BASELINE config C3 at its stated size — 65 536 randomised triple-integrator instances — with the
+    TOTAL fixed and cut into `world` contiguous slices (strong scaling): NCCL scatter of x0 from rank 0,
+    per-rank solve, NCCL gather of the results, each timed on the device (max over ranks); rank 0 then
+    solves all 65 536 instances on its own GPU and checks that the gathered results are the same bits
+    (reference analogue: the nthreads-equivalence tests, test/ilqr/ilqr_class_test.cpp:130-160)."""
+    from altro_cpp_b200.sharding import gather_rows, scatter_rows
+    spec, gen_x0, _, _ = workload("c3")
+    total = 65536
+    per = total // world
+    n, m, N = spec.n, spec.m, spec.N
+    distributed = world > 1
+
+    def timed(fn):
+        torch.cuda.synchronize(dev)
+        if distributed:
+            dist.barrier()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, float(t.item())
+
+    X0_all = torch.from_numpy(gen_x0(spec, total)).to(dev) if rank == 0 else None
+    if distributed:
+        scatter_rows(X0_all, total, (n,), torch.float64, dev)  # warm-up of the NCCL path
+        x0_dev, scatter_ms = timed(lambda: scatter_rows(X0_all, total, (n,), torch.float64, dev))
+    else:
+        x0_dev, scatter_ms = X0_all, 0.0
+    solver = pkg.BatchSolver(spec, per, device=local_rank)
+
+    def step():
+        solver.set_inputs_dev(x0_dev.data_ptr(), 0, spec.u0, stream=stream)
+        solver.solve_al(stream=stream)
+
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(dev)
+        if distributed:
+            dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    Xl = torch.empty((per, N + 1, n), dtype=torch.float64, device=dev)
+    Ul = torch.empty((per, N, m), dtype=torch.float64, device=dev)
+    solver.trajectory_dev(Xl.data_ptr(), Ul.data_ptr())
+    res = solver.results()
+    scal = torch.from_numpy(np.stack([res["cost"], res["viol"], res["status"].astype(np.float64),
+                                      res["iters"][:, 2].astype(np.float64)], axis=1)).to(dev)
+    if distributed:
+        gather_rows(scal, total)  # warm-up
+        (Xg, Ug, Sg), gather_ms = timed(lambda: (gather_rows(Xl, total), gather_rows(Ul, total), gather_rows(scal, total)))
+    else:
+        (Xg, Ug, Sg), gather_ms = (Xl, Ul, scal), 0.0
+    out = None
+    if rank == 0:
+        one = solver if world == 1 else pkg.BatchSolver(spec, total, device=local_rank)
+        if world > 1:
+            one.set_inputs_dev(X0_all.data_ptr(), 0, spec.u0)
+            one.solve_al()
+        X1 = torch.empty((total, N + 1, n), dtype=torch.float64, device=dev)
+        U1 = torch.empty((total, N, m), dtype=torch.float64, device=dev)
+        one.trajectory_dev(X1.data_ptr(), U1.data_ptr())
+        r1 = one.results()
+        S1 = np.stack([r1["cost"], r1["viol"], r1["status"].astype(np.float64), r1["iters"][:, 2].astype(np.float64)], axis=1)
+        same = bool(torch.equal(Xg.view(torch.int64), X1.view(torch.int64)) and torch.equal(Ug.view(torch.int64), U1.view(torch.int64))
+                    and np.array_equal(Sg.cpu().numpy().view(np.int64), S1.view(np.int64)))
+        out = {"workload": "C3: triple integrator n=6 m=2 N=50, goal + control bounds, 65536 instances in total",
+               "scaling": "strong", "global_batch": total, "batch_per_gpu": per, "ms_per_step": ms,
+               "value": total / (ms * 1e-3), "unit": UNIT,
+               "scatter_ms": scatter_ms, "gather_ms": gather_ms,
+               "scatter_bytes": total * n * 8, "gather_bytes": total * ((N + 1) * n + N * m + 4) * 8,
+               "gathered_bit_identical_to_1gpu_solve": same,
+               "solved_fraction": float((S1[:, 2] == 0).mean())}
+        assert same, "sharded results differ from the one-GPU solve of the same instances"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -262,8 +354,18 @@ def main():
     X0_all_dev = None
     if rank == 0:
         X0_all_dev = torch.from_numpy(gen_x0(spec, total)).to(dev)
+    scatter_ms_weak = gather_ms_weak = 0.0
     if distributed:
+        scatter_rows(X0_all_dev, total, (n,), torch.float64, dev)  # warm-up of the NCCL path
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        ts0 = torch.cuda.Event(enable_timing=True)
+        ts1 = torch.cuda.Event(enable_timing=True)
+        ts0.record()
         x0_dev = scatter_rows(X0_all_dev, total, (n,), torch.float64, dev)
+        ts1.record()
+        torch.cuda.synchronize(dev)
+        scatter_ms_weak = ts0.elapsed_time(ts1)
     else:
         x0_dev = X0_all_dev
     X0_host = x0_dev.cpu().numpy()
@@ -402,6 +504,11 @@ def main():
                     "counted, not executed"}}
         del solver2
 
+    # ---- strong scaling at C3's stated size (all ranks take part; reported by rank 0)
+    strong = None
+    if not args.no_extras and args.workload == "c2":
+        strong = strong_scaling_c3(pkg, torch, dist, world, rank, dev, local_rank, stream, max(3, args.steps))
+
     # ---- reduce over ranks: max time, summed work
     t = torch.tensor([ms, ms_e2e, ms_bp if have_bp else 0.0], dtype=torch.float64, device=dev)
     stats = torch.tensor([float((res["status"] == 0).sum()), float(res["iters"][:, 2].sum()),
@@ -413,7 +520,17 @@ def main():
         dist.all_reduce(smax, op=dist.ReduceOp.MAX)
         stats[2] = smax[2]
         # gather per-instance results on rank 0 — the output side of the scatter
-        cost_all = gather_rows(torch.from_numpy(res["cost"]).to(dev).reshape(-1, 1), total)
+        cost_dev = torch.from_numpy(res["cost"]).to(dev).reshape(-1, 1)
+        gather_rows(cost_dev, total)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        tg0 = torch.cuda.Event(enable_timing=True)
+        tg1 = torch.cuda.Event(enable_timing=True)
+        tg0.record()
+        cost_all = gather_rows(cost_dev, total)
+        tg1.record()
+        torch.cuda.synchronize(dev)
+        gather_ms_weak = tg0.elapsed_time(tg1)
         assert rank != 0 or cost_all.shape[0] == total
     ms, ms_e2e, ms_bp_max = [float(v) for v in t.tolist()]
 
@@ -470,6 +587,10 @@ def main():
                              "backward_passes_per_step": float(stats[1].item()),
                              "contract_GBps": float(stats[1].item()) * (bp_bytes / B) / (ms * 1e-3) / 1e9},
             "extras": extras,
+            "strong_scaling": strong,
+            "io": {"scatter_ms": scatter_ms_weak, "gather_ms": gather_ms_weak,
+                   "note": "NCCL scatter of x0 from rank 0 / gather of the per-instance costs to rank 0, outside the "
+                           "timed region (0 on one GPU: the inputs are generated in place)"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

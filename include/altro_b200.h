@@ -258,6 +258,27 @@ int altro_b200_get_scalars_host(altro_b200_solver* s, double* reg, double* dV0, 
                                 double* alpha, double* z, double* dJ, double* grad,
                                 double* penalty, double* initial_cost, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * The same batch sharded over several GPUs of one node (replaces the reference's
+ * SolverOptions::nthreads thread pool, altro/ilqr/ilqr.hpp:354-365, 707-738, one level up):
+ * contiguous slices of the batch, one solver and one host thread per device, no collective.
+ * Per-instance results do not depend on the placement (bit-identical to a one-GPU solve).
+ * ---------------------------------------------------------------------------------- */
+typedef struct altro_b200_multi altro_b200_multi;
+int altro_b200_multi_create(const altro_b200_problem* p, int batch, int use_constraints, const int* devices,
+                            int ndevices, altro_b200_multi** out);
+void altro_b200_multi_destroy(altro_b200_multi* m);
+int altro_b200_multi_num_devices(const altro_b200_multi* m);
+int altro_b200_multi_set_options(altro_b200_multi* m, const altro_b200_options* o);
+/* AugmentedLagrangianiLQR::Solve() for the whole batch with host buffers (layouts as
+ * altro_b200_solve_al_host); blocks until every device is done */
+int altro_b200_multi_solve_al_host(altro_b200_multi* m, const double* x0, const double* U0, const double* u_nominal,
+                                   double* X, double* U, double* cost, double* viol, int32_t* status,
+                                   int32_t* iters);
+/* device time of the last solve per device [ndevices]: inputs H2D + packing, solve, results D2H */
+int altro_b200_multi_last_timings(const altro_b200_multi* m, double* scatter_ms, double* solve_ms,
+                                  double* gather_ms);
+
 /* --- measurement helpers -------------------------------------------------------------
  * Algorithmic bytes of one batched backward pass over the materialised expansions
  * (8*[N*(n(n+m)+n^2+nm+m^2+n+m+mn+m)+n^2+n] per instance). */

@@ -327,6 +327,23 @@ void TestThreeObstacles() {
     for (int i = 0; i < 3; ++i) diff = std::fmax(diff, std::fabs(Z0.State(k)(i) - Z->State(k)(i)));
   EXPECT(diff == 0.0);
   EXPECT(batched.KernelLaunches() > 0);
+
+  // the same batch cut into two slices (two solvers + host threads; here both on device 0): every
+  // instance gets the same bits wherever it is solved
+  altro::augmented_lagrangian::BatchedAugmentedLagrangianiLQR<3, 2> sharded(def.MakeProblem(true), 64, std::vector<int>{0, 0});
+  sharded.SetTrajectory(std::make_shared<altro::Trajectory<3, 2>>(def.InitialTrajectory()));
+  sharded.SetInitialStates(x0);
+  sharded.GetOptions().initial_penalty = 1.0;
+  sharded.Solve();
+  for (int b : {0, 31, 32, 63}) {
+    EXPECT(sharded.GetIterations(b) == batched.GetIterations(b) && sharded.GetStatus(b) == batched.GetStatus(b));
+    EXPECT(sharded.GetCost(b) == batched.GetCost(b));
+    altro::Trajectory<3, 2> Za = batched.GetTrajectory(b), Zb = sharded.GetTrajectory(b);
+    double dz = 0.0;
+    for (int k = 0; k <= def.N; ++k)
+      for (int i = 0; i < 3; ++i) dz = std::fmax(dz, std::fabs(Za.State(k)(i) - Zb.State(k)(i)));
+    EXPECT(dz == 0.0);
+  }
 }
 
 // test/ilqr/ilqr_test.cpp:304-336, test/examples/example_triple_integrator_test.cpp:16-70

@@ -2,12 +2,18 @@
 on identical seeded inputs, plus the reference's golden values straight on the device and
 size-independent properties at BASELINE.json's full batch size.
 
-Tolerances (SURVEY.md 8c (iii), fp64): identical status and iteration counts per instance;
-X, U, cost to <= 1e-9 relative after a whole solve and <= 1e-10 step by step; the gains K, d of
-the LAST backward pass to <= 1e-6 — they are a sensitive function of the iterate (Quu^-1 near
-convergence amplifies the 1e-10 difference of the trajectories), step by step they agree to 1e-9.  The oracle is compiled without FMA contraction, the
-device code with it, so bit equality is not expected; a handful of knife-edge instances may
-take a different discrete decision — the tests bound their fraction.
+Tolerances: identical status and iteration counts per instance — on every
+config and batch measured so far 100 % of the instances follow the oracle's discrete path
+(profiles/r02_parity_stats.txt: 2048 of 2048 on C2 at B = 16384, 1024 of 1024 on C3, 128 of 128 on C4)
+and the tests require exactly that; X and cost to <= 1e-9 relative after a whole solve.  The oracle is
+compiled without FMA contraction, the device code with it, so every iteration starts ~1e-16 apart and
+the difference is amplified by the iteration map: after the 2 iterations of C3 everything agrees to
+1.3e-11; after the 40-70 iterations of a converging C2 instance X agrees to 1.7e-10 and U to 1.4e-9;
+after the 160-200 iterations of a C2 instance that ends in kMaxInnerIterations X agrees to 5.8e-10 and
+U to 5.2e-9; the gains K, d of the LAST backward pass go through Quu^-1 and agree to 2.3e-8 / 4.8e-7
+(maxima over 2048 instances; medians are 1e-13 ... 1e-15).  C4 (cartpole swing-up, 100 iterations, every
+instance stalls) is the most sensitive map: X to 5.4e-8.  The tolerances below are those maxima
+rounded up to the next power of ten; step by step everything agrees to 1e-10 ... 1e-12.
 """
 import numpy as np
 import pytest
@@ -226,7 +232,9 @@ def test_golden_triple_integrator(gpu):
 # ------------------------------------------------------------------------------------------
 # whole solves against the oracle on seeded random batches
 # ------------------------------------------------------------------------------------------
-def compare_batch(gpu, oracle, spec, X0, al=True, options=None, max_mismatch_frac=0.02):
+def compare_batch(gpu, oracle, spec, X0, al=True, options=None, max_mismatch_frac=0.0):
+    """-> (max relative errors over the instances on the oracle's discrete path, fraction NOT on it, ...).
+    No instance is dropped silently: the fraction is returned, printed, and bounded (default: zero)."""
     B = X0.shape[0]
     og = options or gpu.default_options()
     oo = oracle.default_options()
@@ -242,6 +250,7 @@ def compare_batch(gpu, oracle, spec, X0, al=True, options=None, max_mismatch_fra
     ref = oracle.solve_batch(spec, X0, options=oo, use_al=al, nthreads=8)
     same = np.all(r["iters"] == ref["iters"], axis=1) & (r["status"] == ref["status"])
     frac = 1.0 - same.mean()
+    print(f"[parity] {B} instances, {(~same).sum()} off the oracle's discrete path (fraction {frac:.4f})")
     assert frac <= max_mismatch_frac, f"{(~same).sum()} of {B} instances took a different discrete path"
     idx = np.where(same)[0]
     errs = dict(
@@ -262,7 +271,7 @@ def test_solve_unicycle_turn90_ilqr(gpu, oracle):
     assert frac == 0.0
     for k in ("X", "U", "cost"):
         assert errs[k] <= RTOL, errs
-    assert errs["K"] <= 1e-6 and errs["d"] <= 1e-6, errs
+    assert errs["K"] <= 1e-7 and errs["d"] <= 1e-6, errs
 
 
 def test_solve_unicycle_turn90_al(gpu, oracle):
@@ -282,10 +291,11 @@ def test_solve_unicycle_three_obstacles_al(gpu, oracle):
     spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
     X0 = P.perturbed_initial_states(spec, 256, P.UNICYCLE_X0_SCALE)
     errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0)
-    for k in ("X", "U", "cost"):
-        assert errs[k] <= 1e-8, errs
-    assert errs["K"] <= 1e-5 and errs["d"] <= 1e-5, errs
-    assert np.array_equal(r["status"] == 0, ref["status"] == 0)
+    assert frac == 0.0
+    assert errs["X"] <= 1e-9 and errs["cost"] <= 1e-9, errs
+    assert errs["U"] <= 1e-8, errs   # instances that run 160+ iterations (module docstring)
+    assert errs["K"] <= 1e-7 and errs["d"] <= 1e-6, errs
+    assert np.array_equal(r["status"], ref["status"])
 
 
 def test_solve_triple_integrator_al(gpu, oracle):
@@ -293,17 +303,20 @@ def test_solve_triple_integrator_al(gpu, oracle):
     spec = P.triple_integrator_problem(dof=2, N=50, add_constraints=True)
     X0 = P.perturbed_initial_states(spec, 96, P.TRIPLE_INTEGRATOR_X0_SCALE)
     errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0)
+    assert frac == 0.0
     for k in ("X", "U", "cost"):
-        assert errs[k] <= 1e-8, errs
+        assert errs[k] <= 1e-10, errs
+    assert errs["K"] <= 1e-10 and errs["d"] <= 1e-9, errs
 
 
 def test_solve_cartpole_al(gpu, oracle):
     # BASELINE config C4 (model not in the reference: parity is GPU vs oracle only)
     spec = P.cartpole_problem(N=200)
     X0 = P.perturbed_initial_states(spec, 64, P.CARTPOLE_X0_SCALE)
-    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, max_mismatch_frac=0.1)
-    for k in ("X", "U", "cost"):
-        assert errs[k] <= 1e-7, errs
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0)
+    assert frac == 0.0
+    assert errs["X"] <= 1e-7 and errs["cost"] <= 1e-8, errs
+    assert errs["U"] <= 1e-6, errs   # 100 iterations of a swing-up: the most sensitive map (module docstring)
 
 
 # ------------------------------------------------------------------------------------------
@@ -341,6 +354,32 @@ def test_max_iterations_and_status_codes(gpu, oracle):
     errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, options=o, max_mismatch_frac=0.0)
     assert set(np.unique(r["status"])) <= {0, 6, 7}
     assert errs["X"] <= 1e-9
+
+
+def test_full_size_c2_against_the_oracle_on_2048_instances(gpu, oracle):
+    """BASELINE config C2 at its full batch (B = 16384) on the device; the first 2048 instances are also
+    solved by the CPU oracle and compared at trajectory level: every one of them must follow the oracle's
+    discrete path (status + the three iteration counters) and agree in X, U, cost, violation, K, d."""
+    if gpu._test_engine != "phased":
+        pytest.skip("once, on the default engine (the engines are bit-identical, test_engines_are_bit_identical)")
+    import os
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    B, S = 16384, 2048
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, B)
+    s.set_inputs(X0); s.solve_al()
+    r = s.results(); X, U = s.trajectory(); K, d = s.gains()
+    ref = oracle.solve_batch(spec, X0[:S], nthreads=os.cpu_count() or 1)
+    same = np.all(r["iters"][:S] == ref["iters"], axis=1) & (r["status"][:S] == ref["status"])
+    print(f"[parity] full-size C2: {(~same).sum()} of {S} instances off the oracle's discrete path")
+    assert same.all(), f"{(~same).sum()} of {S} instances took a different discrete path"
+    rel = lambda a, b: np.abs(a - b).reshape(S, -1).max(axis=1) / np.maximum(1.0, np.abs(b).reshape(S, -1).max(axis=1))
+    assert rel(X[:S], ref["X"]).max() <= 1e-9
+    assert rel(r["cost"][:S], ref["cost"]).max() <= 1e-9
+    assert np.abs(r["viol"][:S] - ref["viol"]).max() <= 1e-12
+    assert rel(U[:S], ref["U"]).max() <= 1e-8          # see the module docstring for who the worst instances are
+    assert np.percentile(rel(U[:S], ref["U"]), 99) <= 2e-9
+    assert rel(K[:S], ref["K"]).max() <= 1e-7 and rel(d[:S], ref["d"]).max() <= 1e-6
 
 
 def test_full_size_properties_c2(gpu):
@@ -435,12 +474,35 @@ def test_state_limit_and_iteration_caps(gpu, oracle):
 
 
 def test_update_convergence_statistics_stepwise(gpu, oracle):
-    # ilqr.hpp:568-587: dJ, grad and the iteration counters after one manual iteration
+    # ilqr.hpp:568-587: dJ, grad and the iteration counters, iteration by iteration against the oracle's
+    # SolverStats history (cost_decrease, gradient: solver_stats.hpp:54-61)
     spec = P.unicycle_problem(P.K_TURN90)
-    X0 = P.perturbed_initial_states(spec, 32, P.UNICYCLE_X0_SCALE)
-    s = gpu.BatchSolver(spec, 32, use_constraints=False)
+    B = 32
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, B, use_constraints=False)
     s.set_inputs(X0)
-    s.solve_ilqr()  # fills initial_cost etc.; then one more manual iteration on the converged iterate
+    s.solve_setup(); s.rollout(); s.cost()
+    refs = []
+    for b in (0, 7, 31):
+        r = oracle_stepper(oracle, spec, X0[b], False)
+        r.rollout()
+        refs.append((b, r))
+    for it in range(4):
+        s.update_expansions(); s.backward_pass(); s.forward_pass(); s.update_convergence_statistics()
+        sc = s.scalars()
+        iters = s.results()["iters"]
+        assert np.all(iters[:, 0] == it + 1) and np.all(iters[:, 2] == it + 1)
+        for b, r in refs:
+            r.update_expansions(); r.backward_pass(); r.forward_pass(); r.update_convergence_statistics()
+            dJ_o, grad_o = r.stat("cost_decrease"), r.stat("gradient")
+            # the oracle opens a carry-forward row after every iteration: the values of iteration `it` sit in row `it`
+            assert close(sc["dJ"][b], dJ_o[it], 1e-9), (it, b, sc["dJ"][b], dJ_o[it])
+            assert close(sc["grad"][b], grad_o[it], 1e-9), (it, b, sc["grad"][b], grad_o[it])
+            st = r.status()
+            assert st["iterations_inner"] == it + 1 and st["iterations_total"] == it + 1
+    # and on a converged iterate one more manual iteration reports convergence
+    s.set_inputs(X0)
+    s.solve_ilqr()
     it0 = s.results()["iters"].copy()
     s.update_expansions(); s.backward_pass(); s.forward_pass(); s.update_convergence_statistics()
     it1 = s.results()["iters"]

@@ -97,3 +97,20 @@ def test_dense_and_diagonal_cost_paths_agree_bitwise(gpu, monkeypatch):
     b = _solve_like_bench(gpu, spec, X0, solves=1)
     _assert_identical(a, b, 96, "dense vs diagonal cost evaluation")
 
+
+
+def test_sharded_solver_is_bit_identical_to_single(gpu):
+    """altro_b200_multi_*: the batch cut into contiguous slices, one solver + host thread per entry of
+    `devices` (here: three slices on the one GPU a test box has; on an 8-GPU node the same code path with
+    devices = range(8)).  An instance's result does not depend on its slice: bit-identical to one solver."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    B = 1000  # ragged: 334 + 333 + 333
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    one = gpu.BatchSolver(spec, B)
+    a = one.solve_al_host(X0)
+    sharded = gpu.MultiBatchSolver(spec, B, devices=[0, 0, 0])
+    b = sharded.solve_al_host(X0)
+    for k in ("status", "iters", "cost", "viol", "X", "U"):
+        assert np.array_equal(_bits(a[k]), _bits(b[k])), k
+    t = sharded.timings()
+    assert t["solve_ms"].shape == (3,) and np.all(t["solve_ms"] > 0)
