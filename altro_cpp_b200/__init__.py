@@ -5,6 +5,6 @@ this package only marshals arrays to it.  There is no CPU fallback: importing wo
 anywhere, every compute call needs a CUDA device.
 """
 from . import problems  # noqa: F401
-from .capi import BatchSolver, MultiBatchSolver, Options, default_options, lib, SolverError, set_default_engine  # noqa: F401
+from .capi import BatchSolver, MultiBatchSolver, Options, register_model, precompile_model, default_options, lib, SolverError, set_default_engine  # noqa: F401
 
-__all__ = ["problems", "BatchSolver", "MultiBatchSolver", "Options", "default_options", "lib", "SolverError", "set_default_engine"]
+__all__ = ["problems", "BatchSolver", "MultiBatchSolver", "register_model", "precompile_model", "Options", "default_options", "lib", "SolverError", "set_default_engine"]

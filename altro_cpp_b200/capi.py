@@ -65,10 +65,11 @@ def lib():
         L.altro_b200_set_default_engine.argtypes = [ctypes.c_int]
         L.altro_b200_set_default_engine.restype = None
         L.altro_b200_solver_engine.argtypes = [_vp]
-        L.altro_b200_multi_create.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
-                                              ctypes.c_int, ctypes.POINTER(_vp)]
-        L.altro_b200_multi_destroy.argtypes = [_vp]
-        L.altro_b200_multi_num_devices.argtypes = [_vp]
+        if hasattr(L, "altro_b200_multi_create"):  # absent from older builds loaded through ALTRO_B200_LIB
+            L.altro_b200_multi_create.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                                  ctypes.c_int, ctypes.POINTER(_vp)]
+            L.altro_b200_multi_destroy.argtypes = [_vp]
+            L.altro_b200_multi_num_devices.argtypes = [_vp]
         _lib = L
     return _lib
 
@@ -366,3 +367,19 @@ class MultiBatchSolver:
         a, b, c = np.zeros(G), np.zeros(G), np.zeros(G)
         _check(lib().altro_b200_multi_last_timings(self._h, _p(a), _p(b), _p(c)), "multi_last_timings")
         return dict(scatter_ms=a, solve_ms=b, gather_ms=c)
+
+
+def register_model(name: str, cuda_source: str, n: int, m: int, nparams: int = 0) -> int:
+    """Registers a plug-in dynamics model (the CUDA source of a functor struct, concept documented in
+    csrc/device.cuh; example plugins/cartpole.cuh) -> model id for ProblemSpec(model=...)."""
+    mid = ctypes.c_int(-1)
+    rc = lib().altro_b200_register_model(name.encode(), cuda_source.encode(), int(n), int(m), int(nparams), ctypes.byref(mid))
+    _check(rc, "register_model")
+    return mid.value
+
+
+def precompile_model(model_id: int) -> str:
+    """Compiles the model's kernels into the on-disk module cache now (NVRTC; needs no GPU) -> cache file."""
+    buf = ctypes.create_string_buffer(1024)
+    _check(lib().altro_b200_precompile_model(int(model_id), buf, 1024), "precompile_model")
+    return buf.value.decode()

@@ -12,12 +12,21 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <limits>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include "kernels.cuh"
+#include "backward_coop.cuh"
 #include "outer.cuh"
 #include "phased.cuh"
 
@@ -179,191 +188,258 @@ int build_blob(const altro_b200_problem& p, bool use_constraints, std::vector<ch
 // ------------------------------------------------------------------------------------------
 // Kernel dispatch per device-capable model
 // ------------------------------------------------------------------------------------------
+// The kernels of one (model, tile width): either instantiations compiled into this library
+// (handles = host stubs, launched through the runtime) or functions of a module compiled at run
+// time from a plug-in model's source (handles = CUfunction, launched through the driver; modules.inl).
+enum KernelId : int {
+  K_SOLVE = 0, K_PHASE, K_EXP, K_EXP_PHASED, K_CON_VALUES, K_BP_CTG, K_BP_STREAM, K_BP_PHASED,
+  K_COOP_CTG, K_COOP_STREAM, K_COOP_PHASED, K_ROLL_WIDE, K_COST_WIDE, K_ACC_WIDE, K_ROLL_DEEP, K_COST_DEEP,
+  K_ACC_DEEP, K_LS_WIDE, K_LS_DEEP1, K_LS_DEEP2, K_OUTER_REGEN, K_OUTER_ROLLOUT, K_OUTER_DUALS, K_OUTER_COST,
+  K_MICROBENCH, K_NUM
+};
+struct KernelTable {
+  bool driver = false;  // handles are CUfunction (run-time compiled module)
+  int n = 0, m = 0, W = 0;
+  bool coop = false;    // the two-lanes-per-instance backward pass exists for this model
+  const void* f[K_NUM] = {};
+};
+
 struct Ops {
-  cudaError_t (*solve)(const SolverParams&, int mode, int budget, int parts, cudaStream_t);
-  cudaError_t (*phase)(const SolverParams&, int phase, cudaStream_t);
-  cudaError_t (*expansions)(const SolverParams&, cudaStream_t);
-  cudaError_t (*backward_mat)(const SolverParams&, bool store_ctg, cudaStream_t);
-  cudaError_t (*con_values)(const SolverParams&, int k, double* out, cudaStream_t);
-  // phased engine (phased.cuh); nullptr when the tile width has no instantiation
-  cudaError_t (*expansions_phased)(const SolverParams&, cudaStream_t) = nullptr;
-  cudaError_t (*backward_phased)(const SolverParams&, cudaStream_t) = nullptr;
-  cudaError_t (*ls_wide)(const SolverParams&, int mode, cudaStream_t) = nullptr;
-  cudaError_t (*ls_deep)(const SolverParams&, int mode, int max_instances, cudaStream_t) = nullptr;
+  std::function<cudaError_t(const SolverParams&, int mode, int budget, int parts, cudaStream_t)> solve;
+  std::function<cudaError_t(const SolverParams&, int phase, cudaStream_t)> phase;
+  std::function<cudaError_t(const SolverParams&, cudaStream_t)> expansions;
+  std::function<cudaError_t(const SolverParams&, bool store_ctg, cudaStream_t)> backward_mat;
+  std::function<cudaError_t(const SolverParams&, int k, double* out, cudaStream_t)> con_values;
+  // phased engine (phased.cuh); empty when the tile width has no instantiation
+  std::function<cudaError_t(const SolverParams&, cudaStream_t)> expansions_phased;
+  std::function<cudaError_t(const SolverParams&, cudaStream_t)> backward_phased;
+  std::function<cudaError_t(const SolverParams&, int mode, cudaStream_t)> ls_wide;
+  std::function<cudaError_t(const SolverParams&, int mode, int max_instances, cudaStream_t)> ls_deep;
   // outer-loop work of the phased engine on a dense list (outer.cuh); returns the kernels launched
-  cudaError_t (*outer_step)(const SolverParams&, int mode, int sm_count, cudaStream_t, int* nlaunch) = nullptr;
-  cudaError_t (*microbench)(const SolverParams&, double* sink, long long* out, int reps, cudaStream_t) = nullptr;
+  std::function<cudaError_t(const SolverParams&, int mode, int sm_count, cudaStream_t, int* nlaunch)> outer_step;
+  std::function<cudaError_t(const SolverParams&, double* sink, long long* out, int reps, cudaStream_t)> microbench;
   // split line search: rollout / per-knot cost / acceptance kernels (wide: all tiles; deep: the list)
-  cudaError_t (*ls_split_wide)(const SolverParams&, int mode, cudaStream_t) = nullptr;
-  cudaError_t (*ls_split_deep)(const SolverParams&, int mode, int max_instances, cudaStream_t) = nullptr;
+  std::function<cudaError_t(const SolverParams&, int mode, cudaStream_t)> ls_split_wide;
+  std::function<cudaError_t(const SolverParams&, int mode, int max_instances, cudaStream_t)> ls_split_deep;
   bool large = false;  // one instance per CTA (large.cuh): whole solves only, W = 1 layout
 };
 
 constexpr int kBpStages = 4;
+constexpr int kCoopStages = 3;  // ring depth of the two-lanes-per-instance backward pass (47 KB per warp at n = 6)
 constexpr int kPhasedTile = 8;  // tile width of the phased engine's workspaces
 constexpr int kCostGrid = 148 * 12;  // persistent CTAs of the per-knot cost kernels
 
+// models whose backward pass runs two lanes per instance (backward_coop.cuh): medium n with even n and m,
+// tile width 8
+constexpr bool use_coop(int n, int m, int W) {
+  return W == kCoopTile && n >= 5 && n <= 12 && n % kCoopLanes == 0 && m % kCoopLanes == 0;
+}
 template <class M, int W>
-int solve_smem(const SolverParams& P) {
-  return ((P.blob_bytes + 15) / 16) * 16 + kSolveWarps * stage_doubles<M>(P.pmax, W) * sizeof(double);
+constexpr bool kUseCoop = use_coop(M::n, M::m, W);
+
+cudaError_t driver_launch(const void* fn, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args);  // modules.inl
+
+// one launch, whichever kind of handle the table holds
+cudaError_t launch(const KernelTable& kt, int id, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args) {
+  if (!kt.f[id]) return cudaErrorInvalidDeviceFunction;
+  if (kt.driver) return driver_launch(kt.f[id], grid, block, smem, st, args);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kt.f[id], cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  return cudaLaunchKernel(kt.f[id], grid, block, args, smem, st);
+}
+
+// shared-memory sizes of the kernels from the run-time dimensions (the same formulas as the
+// constexpr helpers next to the kernels: stage_doubles, p_stage_doubles, p_roll_stage_doubles, ...)
+struct Dims {
+  int n, m, nz, nkd, nexp;
+  Dims(int n_, int m_) : n(n_), m(m_), nz(n_ + m_), nkd(m_ * n_ + m_), nexp(exp_fields(n_, m_)) {}
+  int stage(int pmax, int W) const {
+    const int fwd = (nz + nkd + pmax) * W, bwd = (nz + pmax) * kWarp;
+    return 2 * (fwd > bwd ? fwd : bwd);
+  }
+  int p_stage(int pmax, int WI) const { return 2 * (nz + nkd + pmax) * WI; }
+  int p_roll_stage(int WI) const { return kRollStages * (nz + nkd) * WI; }
+  int p_deep_warp(int pmax, int N, int WI) const { return p_stage(pmax, WI) + WI * N; }
+  int coop_smem() const {  // backward_coop_smem<M, kCoopStages>()
+    const int scratch = n * n + m * n + n * m + m * m + m + m * n + n + 1;
+    return kCoopStages * nexp * kCoopInst * 8 + kCoopInst * scratch * 8 + kCoopStages * 8;
+  }
+};
+
+Ops make_ops_from(const KernelTable& kt) {
+  Ops o;
+  const Dims D(kt.n, kt.m);
+  const int W = kt.W;
+  auto blob16 = [](const SolverParams& P) { return ((P.blob_bytes + 15) / 16) * 16; };
+  auto arg = [](const void* p) { return const_cast<void*>(p); };
+  o.solve = [=](const SolverParams& P, int mode, int budget, int parts, cudaStream_t st) -> cudaError_t {
+    const size_t smem = blob16(P) + kSolveWarps * D.stage(P.pmax, W) * sizeof(double);
+    void* args[] = {arg(&P), &mode, &budget, &parts};
+    return launch(kt, K_SOLVE, (P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st, args);
+  };
+  o.phase = [=](const SolverParams& P, int phase, cudaStream_t st) -> cudaError_t {
+    const size_t smem = blob16(P) + kSolveWarps * D.stage(P.pmax, W) * sizeof(double);
+    void* args[] = {arg(&P), &phase};
+    return launch(kt, K_PHASE, (P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st, args);
+  };
+  o.expansions = [=](const SolverParams& P, cudaStream_t st) -> cudaError_t {
+    void* args[] = {arg(&P)};
+    return launch(kt, K_EXP, dim3((P.B + 127) / 128, P.N + 1), 128, 0, st, args);
+  };
+  o.con_values = [=](const SolverParams& P, int k, double* out, cudaStream_t st) -> cudaError_t {
+    void* args[] = {arg(&P), &k, &out};
+    return launch(kt, K_CON_VALUES, (P.B + 127) / 128, 128, P.blob_bytes, st, args);
+  };
+  auto backward = [=](const SolverParams& P, int id_mat, int id_coop, cudaStream_t st) -> cudaError_t {
+    void* args[] = {arg(&P)};
+    if (kt.coop && !std::getenv("ALTRO_B200_NO_COOP"))  // medium n: two lanes per instance (backward_coop.cuh)
+      return launch(kt, id_coop, (P.T + kCoopInst / kCoopTile - 1) / (kCoopInst / kCoopTile), kWarp, D.coop_smem(), st, args);
+    const size_t smem = kBpStages * D.nexp * kWarp * sizeof(double) + kBpStages * 8;
+    return launch(kt, id_mat, (P.T + kWarp / W - 1) / (kWarp / W), kWarp, smem, st, args);
+  };
+  o.backward_mat = [=](const SolverParams& P, bool store_ctg, cudaStream_t st) -> cudaError_t {
+    return store_ctg ? backward(P, K_BP_CTG, K_COOP_CTG, st) : backward(P, K_BP_STREAM, K_COOP_STREAM, st);
+  };
+  if (W != kPhasedTile) return o;
+  o.microbench = [=](const SolverParams& P, double* sink, long long* out, int reps, cudaStream_t st) -> cudaError_t {
+    void* args[] = {arg(&P), &sink, &out, &reps};
+    return launch(kt, K_MICROBENCH, 1, kWarp, P.blob_bytes, st, args);
+  };
+  o.expansions_phased = [=](const SolverParams& P, cudaStream_t st) -> cudaError_t {
+    void* args[] = {arg(&P)};
+    return launch(kt, K_EXP_PHASED, dim3((P.B + 127) / 128, P.N + 1), 128, 0, st, args);
+  };
+  o.backward_phased = [=](const SolverParams& P, cudaStream_t st) -> cudaError_t {
+    return backward(P, K_BP_PHASED, K_COOP_PHASED, st);
+  };
+  o.ls_split_wide = [=](const SolverParams& P, int mode, cudaStream_t st) -> cudaError_t {
+    const size_t smem_roll = blob16(P) + kLsWarps * D.p_roll_stage(W) * sizeof(double);
+    const size_t smem_acc = kLsWarps * W * P.N * sizeof(double);
+    const int grid = (P.T + kLsWarps - 1) / kLsWarps;
+    void* a1[] = {arg(&P)};
+    cudaError_t e = launch(kt, K_ROLL_WIDE, grid, kLsWarps * kWarp, smem_roll, st, a1);
+    if (e != cudaSuccess) return e;
+    const long items = static_cast<long>(P.T) * (P.N + 1);
+    const int cgrid = static_cast<int>(std::min<long>((items + kLsWarps - 1) / kLsWarps, kCostGrid));
+    e = launch(kt, K_COST_WIDE, cgrid, kLsWarps * kWarp, P.blob_bytes, st, a1);
+    if (e != cudaSuccess) return e;
+    void* a2[] = {arg(&P), &mode};
+    return launch(kt, K_ACC_WIDE, grid, kLsWarps * kWarp, smem_acc, st, a2);
+  };
+  o.ls_split_deep = [=](const SolverParams& P, int mode, int max_instances, cudaStream_t st) -> cudaError_t {
+    const size_t smem_roll = blob16(P) + kLsWarps * D.p_roll_stage(1) * sizeof(double);
+    const size_t smem_acc = kLsWarps * P.N * sizeof(double);
+    const int grid = (max_instances + kLsWarps - 1) / kLsWarps;
+    int wide_tries = kWarp / W;
+    void* a1[] = {arg(&P), &wide_tries};
+    cudaError_t e = launch(kt, K_ROLL_DEEP, grid, kLsWarps * kWarp, smem_roll, st, a1);
+    if (e != cudaSuccess) return e;
+    const long items = static_cast<long>(max_instances) * (P.N + 1);
+    const int cgrid = static_cast<int>(std::min<long>((items + kLsWarps - 1) / kLsWarps, kCostGrid));
+    e = launch(kt, K_COST_DEEP, cgrid, kLsWarps * kWarp, P.blob_bytes, st, a1);
+    if (e != cudaSuccess) return e;
+    void* a2[] = {arg(&P), &mode, &wide_tries};
+    return launch(kt, K_ACC_DEEP, grid, kLsWarps * kWarp, smem_acc, st, a2);
+  };
+  o.ls_wide = [=](const SolverParams& P, int mode, cudaStream_t st) -> cudaError_t {
+    const size_t smem = blob16(P) + kLsWarps * D.p_stage(P.pmax, W) * sizeof(double);
+    void* args[] = {arg(&P), &mode};
+    return launch(kt, K_LS_WIDE, (P.T + kLsWarps - 1) / kLsWarps, kLsWarps * kWarp, smem, st, args);
+  };
+  o.outer_step = [=](const SolverParams& P, int mode, int sm_count, cudaStream_t st, int* nlaunch) -> cudaError_t {
+    // grids: enough CTAs for every instance to have outer work pending (first slot of a solve),
+    // capped at a few waves; the kernels loop over the device-side list with a grid stride
+    const int nk = P.N + 1;
+    const int lane_grid = std::min((P.B + kOuterThreads - 1) / kOuterThreads, sm_count * 8);
+    const long items = static_cast<long>(P.B) * nk;
+    const int item_grid = static_cast<int>(std::min<long>((items + kOuterThreads - 1) / kOuterThreads, sm_count * 16));
+    int force = std::getenv("ALTRO_B200_ALWAYS_ROLLOUT") ? 1 : 0;
+    void* a1[] = {arg(&P)};
+    void* a2[] = {arg(&P), &force};
+    k_outer_select<<<(P.B + 255) / 256, 256, 0, st>>>(P);
+    cudaError_t e = launch(kt, K_OUTER_REGEN, lane_grid, kOuterThreads, 0, st, a2);
+    if (e == cudaSuccess) e = launch(kt, K_OUTER_DUALS, item_grid, kOuterThreads, 0, st, a1);
+    k_outer_decide<<<lane_grid, kOuterThreads, 0, st>>>(P);
+    if (e == cudaSuccess) e = launch(kt, K_OUTER_ROLLOUT, lane_grid, kOuterThreads, 0, st, a2);
+    if (e == cudaSuccess) e = launch(kt, K_OUTER_COST, item_grid, kOuterThreads, 0, st, a1);
+    k_outer_finish<<<lane_grid, kOuterThreads, 0, st>>>(P, mode);
+    *nlaunch = 7;
+    return e != cudaSuccess ? e : cudaGetLastError();
+  };
+  o.ls_deep = [=](const SolverParams& P, int mode, int max_instances, cudaStream_t st) -> cudaError_t {
+    int wide_tries = kWarp / W;
+    void* args[] = {arg(&P), &mode, &wide_tries};
+    if (P.opt.line_search_max_iterations - kWarp / W <= kWarp / 2) {  // two instances per warp
+      const size_t smem = blob16(P) + kLsWarps * D.p_deep_warp(P.pmax, P.N, 2) * sizeof(double);
+      return launch(kt, K_LS_DEEP2, (max_instances + 2 * kLsWarps - 1) / (2 * kLsWarps), kLsWarps * kWarp, smem, st, args);
+    }
+    const size_t smem = blob16(P) + kLsWarps * D.p_deep_warp(P.pmax, P.N, 1) * sizeof(double);
+    return launch(kt, K_LS_DEEP1, (max_instances + kLsWarps - 1) / kLsWarps, kLsWarps * kWarp, smem, st, args);
+  };
+  return o;
+}
+
+// kernel table of an instantiation compiled into this library
+template <class M, int W>
+KernelTable builtin_table() {
+  KernelTable kt;
+  kt.n = M::n; kt.m = M::m; kt.W = W;
+  kt.f[K_SOLVE] = reinterpret_cast<const void*>(k_solve<M, W>);
+  kt.f[K_PHASE] = reinterpret_cast<const void*>(k_phase<M, W>);
+  kt.f[K_EXP] = reinterpret_cast<const void*>(k_update_expansions<M, W, false>);
+  kt.f[K_CON_VALUES] = reinterpret_cast<const void*>(k_constraint_values<M, W>);
+  kt.f[K_BP_CTG] = reinterpret_cast<const void*>(k_backward_mat<M, W, kBpStages, true, false>);
+  kt.f[K_BP_STREAM] = reinterpret_cast<const void*>(k_backward_mat<M, W, kBpStages, false, false>);
+  if constexpr (W == kPhasedTile) {
+    kt.f[K_EXP_PHASED] = reinterpret_cast<const void*>(k_update_expansions<M, W, true>);
+    kt.f[K_BP_PHASED] = reinterpret_cast<const void*>(k_backward_mat<M, W, kBpStages, false, true>);
+    if constexpr (kUseCoop<M, W>) {
+      kt.coop = true;
+      kt.f[K_COOP_CTG] = reinterpret_cast<const void*>(k_backward_coop<M, kCoopStages, true, false>);
+      kt.f[K_COOP_STREAM] = reinterpret_cast<const void*>(k_backward_coop<M, kCoopStages, false, false>);
+      kt.f[K_COOP_PHASED] = reinterpret_cast<const void*>(k_backward_coop<M, kCoopStages, false, true>);
+    }
+    kt.f[K_ROLL_WIDE] = reinterpret_cast<const void*>(k_roll_wide<M, W>);
+    kt.f[K_COST_WIDE] = reinterpret_cast<const void*>(k_cost_wide<M, W>);
+    kt.f[K_ACC_WIDE] = reinterpret_cast<const void*>(k_acc_wide<M, W>);
+    kt.f[K_ROLL_DEEP] = reinterpret_cast<const void*>(k_roll_deep<M, W>);
+    kt.f[K_COST_DEEP] = reinterpret_cast<const void*>(k_cost_deep<M, W>);
+    kt.f[K_ACC_DEEP] = reinterpret_cast<const void*>(k_acc_deep<M, W>);
+    kt.f[K_LS_WIDE] = reinterpret_cast<const void*>(k_ls_wide<M, W>);
+    kt.f[K_LS_DEEP1] = reinterpret_cast<const void*>(k_ls_deep<M, W, 1>);
+    kt.f[K_LS_DEEP2] = reinterpret_cast<const void*>(k_ls_deep<M, W, 2>);
+    kt.f[K_OUTER_REGEN] = reinterpret_cast<const void*>(k_outer_rollout<M, W, true>);
+    kt.f[K_OUTER_ROLLOUT] = reinterpret_cast<const void*>(k_outer_rollout<M, W, false>);
+    kt.f[K_OUTER_DUALS] = reinterpret_cast<const void*>(k_outer_duals<M, W>);
+    kt.f[K_OUTER_COST] = reinterpret_cast<const void*>(k_outer_cost<M, W>);
+    kt.f[K_MICROBENCH] = reinterpret_cast<const void*>(k_microbench<M, W>);
+  }
+  return kt;
 }
 
 template <class M, int W>
 Ops make_ops() {
-  Ops o;
-  o.solve = [](const SolverParams& P, int mode, int budget, int parts, cudaStream_t st) -> cudaError_t {
-    const int smem = solve_smem<M, W>(P);
-    cudaError_t e = cudaFuncSetAttribute(k_solve<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    k_solve<M, W><<<(P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st>>>(P, mode, budget, parts);
-    return cudaGetLastError();
-  };
-  o.phase = [](const SolverParams& P, int phase, cudaStream_t st) -> cudaError_t {
-    const int smem = solve_smem<M, W>(P);
-    cudaError_t e = cudaFuncSetAttribute(k_phase<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    k_phase<M, W><<<(P.T + kSolveWarps - 1) / kSolveWarps, kSolveWarps * kWarp, smem, st>>>(P, phase);
-    return cudaGetLastError();
-  };
-  o.expansions = [](const SolverParams& P, cudaStream_t st) -> cudaError_t {
-    dim3 grid((P.B + 127) / 128, P.N + 1);
-    k_update_expansions<M, W><<<grid, 128, 0, st>>>(P);
-    return cudaGetLastError();
-  };
-  o.con_values = [](const SolverParams& P, int k, double* out, cudaStream_t st) -> cudaError_t {
-    k_constraint_values<M, W><<<(P.B + 127) / 128, 128, P.blob_bytes, st>>>(P, k, out);
-    return cudaGetLastError();
-  };
-  o.backward_mat = [](const SolverParams& P, bool store_ctg, cudaStream_t st) -> cudaError_t {
-    const int smem = kBpStages * Lane<M, W>::nexp * kWarp * sizeof(double) + kBpStages * 8;
-    const int grid = (P.T + kWarp / W - 1) / (kWarp / W);
-    cudaError_t e;
-    if (store_ctg) {
-      e = cudaFuncSetAttribute(k_backward_mat<M, W, kBpStages, true>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      k_backward_mat<M, W, kBpStages, true><<<grid, kWarp, smem, st>>>(P);
-    } else {
-      e = cudaFuncSetAttribute(k_backward_mat<M, W, kBpStages, false>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      k_backward_mat<M, W, kBpStages, false><<<grid, kWarp, smem, st>>>(P);
-    }
-    return cudaGetLastError();
-  };
-  if constexpr (W == kPhasedTile) {
-    o.microbench = [](const SolverParams& P, double* sink, long long* out, int reps, cudaStream_t st) -> cudaError_t {
-      k_microbench<M, W><<<1, kWarp, P.blob_bytes, st>>>(P, sink, out, reps);
-      return cudaGetLastError();
-    };
-    o.expansions_phased = [](const SolverParams& P, cudaStream_t st) -> cudaError_t {
-      dim3 grid((P.B + 127) / 128, P.N + 1);
-      k_update_expansions<M, W, true><<<grid, 128, 0, st>>>(P);
-      return cudaGetLastError();
-    };
-    o.backward_phased = [](const SolverParams& P, cudaStream_t st) -> cudaError_t {
-      const int smem = kBpStages * Lane<M, W>::nexp * kWarp * sizeof(double) + kBpStages * 8;
-      const int grid = (P.T + kWarp / W - 1) / (kWarp / W);
-      cudaError_t e = cudaFuncSetAttribute(k_backward_mat<M, W, kBpStages, false, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      k_backward_mat<M, W, kBpStages, false, true><<<grid, kWarp, smem, st>>>(P);
-      return cudaGetLastError();
-    };
-    o.ls_split_wide = [](const SolverParams& P, int mode, cudaStream_t st) -> cudaError_t {
-      const int blob = ((P.blob_bytes + 15) / 16) * 16;
-      const int smem_roll = blob + kLsWarps * p_roll_stage_doubles<M>(W) * sizeof(double);
-      const int smem_acc = kLsWarps * W * P.N * sizeof(double);
-      cudaError_t e = cudaFuncSetAttribute(k_roll_wide<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll);
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(k_acc_wide<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_acc);
-      if (e != cudaSuccess) return e;
-      const int grid = (P.T + kLsWarps - 1) / kLsWarps;
-      k_roll_wide<M, W><<<grid, kLsWarps * kWarp, smem_roll, st>>>(P);
-      const long items = static_cast<long>(P.T) * (P.N + 1);
-      const int cgrid = static_cast<int>(std::min<long>((items + kLsWarps - 1) / kLsWarps, kCostGrid));
-      k_cost_wide<M, W><<<cgrid, kLsWarps * kWarp, P.blob_bytes, st>>>(P);
-      k_acc_wide<M, W><<<grid, kLsWarps * kWarp, smem_acc, st>>>(P, mode);
-      return cudaGetLastError();
-    };
-    o.ls_split_deep = [](const SolverParams& P, int mode, int max_instances, cudaStream_t st) -> cudaError_t {
-      const int blob = ((P.blob_bytes + 15) / 16) * 16;
-      const int smem_roll = blob + kLsWarps * p_roll_stage_doubles<M>(1) * sizeof(double);
-      const int smem_acc = kLsWarps * P.N * sizeof(double);
-      cudaError_t e = cudaFuncSetAttribute(k_roll_deep<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_roll);
-      if (e != cudaSuccess) return e;
-      const int grid = (max_instances + kLsWarps - 1) / kLsWarps;
-      k_roll_deep<M, W><<<grid, kLsWarps * kWarp, smem_roll, st>>>(P, kWarp / W);
-      const long items = static_cast<long>(max_instances) * (P.N + 1);
-      const int cgrid = static_cast<int>(std::min<long>((items + kLsWarps - 1) / kLsWarps, kCostGrid));
-      k_cost_deep<M, W><<<cgrid, kLsWarps * kWarp, P.blob_bytes, st>>>(P, kWarp / W);
-      k_acc_deep<M, W><<<grid, kLsWarps * kWarp, smem_acc, st>>>(P, mode, kWarp / W);
-      return cudaGetLastError();
-    };
-    o.ls_wide = [](const SolverParams& P, int mode, cudaStream_t st) -> cudaError_t {
-      const int smem = ((P.blob_bytes + 15) / 16) * 16 + kLsWarps * p_stage_doubles<M>(P.pmax, W) * sizeof(double);
-      cudaError_t e = cudaFuncSetAttribute(k_ls_wide<M, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      if (e != cudaSuccess) return e;
-      k_ls_wide<M, W><<<(P.T + kLsWarps - 1) / kLsWarps, kLsWarps * kWarp, smem, st>>>(P, mode);
-      return cudaGetLastError();
-    };
-    o.outer_step = [](const SolverParams& P, int mode, int sm_count, cudaStream_t st, int* nlaunch) -> cudaError_t {
-      // grids: enough CTAs for every instance to have outer work pending (first slot of a solve),
-      // capped at a few waves; the kernels loop over the device-side list with a grid stride
-      const int nk = P.N + 1;
-      const int lane_grid = std::min((P.B + kOuterThreads - 1) / kOuterThreads, sm_count * 8);
-      const long items = static_cast<long>(P.B) * nk;
-      const int item_grid = static_cast<int>(std::min<long>((items + kOuterThreads - 1) / kOuterThreads, sm_count * 16));
-      k_outer_select<<<(P.B + 255) / 256, 256, 0, st>>>(P);
-      const int force = std::getenv("ALTRO_B200_ALWAYS_ROLLOUT") ? 1 : 0;
-      k_outer_rollout<M, W, true><<<lane_grid, kOuterThreads, 0, st>>>(P, force);
-      k_outer_duals<M, W><<<item_grid, kOuterThreads, 0, st>>>(P);
-      k_outer_decide<<<lane_grid, kOuterThreads, 0, st>>>(P);
-      k_outer_rollout<M, W, false><<<lane_grid, kOuterThreads, 0, st>>>(P, force);
-      k_outer_cost<M, W><<<item_grid, kOuterThreads, 0, st>>>(P);
-      k_outer_finish<<<lane_grid, kOuterThreads, 0, st>>>(P, mode);
-      *nlaunch = 7;
-      return cudaGetLastError();
-    };
-    o.ls_deep = [](const SolverParams& P, int mode, int max_instances, cudaStream_t st) -> cudaError_t {
-      const int blob = ((P.blob_bytes + 15) / 16) * 16;
-      if (P.opt.line_search_max_iterations - kWarp / W <= kWarp / 2) {  // two instances per warp
-        const int smem = blob + kLsWarps * p_deep_warp_doubles<M>(P.pmax, P.N, 2) * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(k_ls_deep<M, W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        k_ls_deep<M, W, 2><<<(max_instances + 2 * kLsWarps - 1) / (2 * kLsWarps), kLsWarps * kWarp, smem, st>>>(P, mode, kWarp / W);
-      } else {
-        const int smem = blob + kLsWarps * p_deep_warp_doubles<M>(P.pmax, P.N, 1) * sizeof(double);
-        cudaError_t e = cudaFuncSetAttribute(k_ls_deep<M, W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        k_ls_deep<M, W, 1><<<(max_instances + kLsWarps - 1) / kLsWarps, kLsWarps * kWarp, smem, st>>>(P, mode, kWarp / W);
-      }
-      return cudaGetLastError();
-    };
-  }
-  return o;
+  return make_ops_from(builtin_table<M, W>());
 }
+
+#include "modules.inl"
 
 Ops make_large_ops_32_8() {
   Ops o;
   o.large = true;
-  o.phase = nullptr;
-  o.expansions = nullptr;
-  o.backward_mat = nullptr;
-  o.con_values = nullptr;
   o.solve = [](const SolverParams& P, int mode, int, int, cudaStream_t st) -> cudaError_t {
     return altro_b200_launch_solve_large_32_8(P, mode, st);
   };
   return o;
 }
 
-// Tile widths with instantiations.  ALTRO_DEV_BUILD (altro_cpp_b200/build.py --dev): the unicycle at
-// the phased engine's tile width only — a kernel-tuning build that compiles in well under a minute.
-#ifdef ALTRO_DEV_BUILD
+// Tile widths with instantiations: one.  Round 1 compiled five widths x four models x ~20 kernels
+// eagerly (46 MB, 3.6 - 15 minutes); the phased engine only ever used width 8 and the fused engine — kept
+// as its cross-check — runs on it too.  ALTRO_DEV_BUILD (altro_cpp_b200/build.py --dev) additionally
+// restricts the models to the unicycle: a kernel-tuning build.
 constexpr int kWidths[] = {8};
-#else
-constexpr int kWidths[] = {2, 4, 8, 16, 32};
-#endif
 bool width_available(int W) {
   for (int w : kWidths)
     if (w == W) return true;
@@ -373,26 +449,59 @@ bool width_available(int W) {
 template <class M>
 bool ops_for_width(int W, Ops* out) {
   if (!width_available(W)) return false;
-#ifndef ALTRO_DEV_BUILD
-  if (W == 2) { if (out) *out = make_ops<M, 2>(); return true; }
-  if (W == 4) { if (out) *out = make_ops<M, 4>(); return true; }
-  if (W == 16) { if (out) *out = make_ops<M, 16>(); return true; }
-  if (W == 32) { if (out) *out = make_ops<M, 32>(); return true; }
-#endif
   if (W == 8) { if (out) *out = make_ops<M, 8>(); return true; }
   return false;
 }
 
-bool lookup_ops(int n, int m, int model, int W, Ops* out) {
-  if (model == kUnicycle && n == 3 && m == 2) return ops_for_width<Unicycle>(W, out);
-#ifndef ALTRO_DEV_BUILD
-  if (model == kTripleIntegrator && n == 6 && m == 2) return ops_for_width<TripleIntegrator<2>>(W, out);
-  if (model == kTripleIntegrator && n == 3 && m == 1) return ops_for_width<TripleIntegrator<1>>(W, out);
-  if (model == kCartpole && n == 4 && m == 1) return ops_for_width<Cartpole>(W, out);
-  if (model == kLinear && n == 32 && m == 8) { if (out) *out = make_large_ops_32_8(); return true; }
-#endif
-  return false;
+// The cart-pole ships as a plug-in (plugins/cartpole.cuh): ALTRO_B200_MODEL_CARTPOLE resolves to its id.
+int builtin_cartpole_id() {
+  static int id = -1;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const std::string text = read_file(library_dir() + "/plugins/cartpole.cuh");
+    if (text.empty()) return;
+    std::lock_guard<std::mutex> lock(g_plugin_mutex);
+    PluginModel pm;
+    pm.name = "Cartpole";
+    pm.source = text;
+    pm.n = 4; pm.m = 1; pm.nparams = 4;
+    g_plugins.push_back(pm);
+    id = kFirstPluginId + static_cast<int>(g_plugins.size()) - 1;
+  });
+  return id;
 }
+int resolve_model(int model) { return model == kCartpole ? builtin_cartpole_id() : model; }
+
+// out == nullptr: is there a device path for (n, m, model) at tile width W?  (no compilation, no device)
+// Otherwise fills *out; for a plug-in model that may compile or load its module on the CURRENT device.
+int lookup_ops_rc(int n, int m, int model, int W, Ops* out) {
+  model = resolve_model(model);
+  if (model >= kFirstPluginId) {
+    {
+      std::lock_guard<std::mutex> lock(g_plugin_mutex);
+      const int idx = model - kFirstPluginId;
+      if (idx >= static_cast<int>(g_plugins.size()) || g_plugins[idx].n != n || g_plugins[idx].m != m || W != kPhasedTile)
+        return ALTRO_B200_ERR_UNSUPPORTED;
+    }
+    if (!out) return 0;
+    int device = 0;
+    cudaGetDevice(&device);
+    return plugin_ops(model, device, out);
+  }
+#ifdef ALTRO_DEV_TI2  // kernel-tuning build for the n = 6 path
+  if (model == kTripleIntegrator && n == 6 && m == 2) return ops_for_width<TripleIntegrator<2>>(W, out) ? 0 : ALTRO_B200_ERR_UNSUPPORTED;
+  return ALTRO_B200_ERR_UNSUPPORTED;
+#endif
+  bool ok = false;
+  if (model == kUnicycle && n == 3 && m == 2) ok = ops_for_width<Unicycle>(W, out);
+#ifndef ALTRO_DEV_BUILD
+  else if (model == kTripleIntegrator && n == 6 && m == 2) ok = ops_for_width<TripleIntegrator<2>>(W, out);
+  else if (model == kTripleIntegrator && n == 3 && m == 1) ok = ops_for_width<TripleIntegrator<1>>(W, out);
+  else if (model == kLinear && n == 32 && m == 8) { if (out) *out = make_large_ops_32_8(); ok = true; }
+#endif
+  return ok ? 0 : ALTRO_B200_ERR_UNSUPPORTED;
+}
+bool lookup_ops(int n, int m, int model, int W, Ops* out) { return lookup_ops_rc(n, m, model, W, out) == 0; }
 
 // Tile width: the serial sweeps are latency-bound, so a B200 wants >= ~14 warps per SM in flight.
 // Narrow tiles turn a small batch into more warps and free lane groups for the parallel line
@@ -674,6 +783,50 @@ void altro_b200_default_options(altro_b200_options* o) {  // solver_options.hpp:
 
 int altro_b200_is_supported(int n, int m, int model) { return lookup_ops(n, m, model, kPhasedTile, nullptr) ? 1 : 0; }
 
+// ---------------------------------------------------------------- plug-in models
+int altro_b200_register_model(const char* name, const char* cuda_source, int n, int m, int nparams, int* model_id) {
+  if (!name || !cuda_source || !model_id || n <= 0 || m <= 0 || n > 16 || m > 16 || nparams < 0)
+    return fail(ALTRO_B200_ERR_ARG, "register_model: bad argument (1 <= n, m <= 16)");
+  const std::string nm = name;
+  if (nm.empty() || !(std::isalpha(static_cast<unsigned char>(nm[0])) || nm[0] == '_'))
+    return fail(ALTRO_B200_ERR_ARG, "register_model: the name must be a C++ identifier");
+  for (char c : nm)
+    if (!(std::isalnum(static_cast<unsigned char>(c)) || c == '_')) return fail(ALTRO_B200_ERR_ARG, "register_model: the name must be a C++ identifier");
+  if (std::string(cuda_source).find("struct " + nm) == std::string::npos)
+    return fail(ALTRO_B200_ERR_ARG, "register_model: the source must define `struct " + nm + "`");
+  std::lock_guard<std::mutex> lock(g_plugin_mutex);
+  for (size_t i = 0; i < g_plugins.size(); ++i)
+    if (g_plugins[i].name == nm) {
+      if (g_plugins[i].source != cuda_source || g_plugins[i].n != n || g_plugins[i].m != m || g_plugins[i].nparams != nparams)
+        return fail(ALTRO_B200_ERR_STATE, "register_model: a different model named '" + nm + "' is already registered");
+      *model_id = kFirstPluginId + static_cast<int>(i);
+      return 0;
+    }
+  PluginModel pm;
+  pm.name = nm;
+  pm.source = cuda_source;
+  pm.n = n; pm.m = m; pm.nparams = nparams;
+  g_plugins.push_back(pm);
+  *model_id = kFirstPluginId + static_cast<int>(g_plugins.size()) - 1;
+  return 0;
+}
+int altro_b200_precompile_model(int model, char* cache_path, int cache_path_cap) {
+  model = resolve_model(model);
+  PluginModel pm;
+  {
+    std::lock_guard<std::mutex> lock(g_plugin_mutex);
+    const int idx = model - kFirstPluginId;
+    if (idx < 0 || idx >= static_cast<int>(g_plugins.size())) return fail(ALTRO_B200_ERR_ARG, "precompile_model: not a plug-in model id");
+    pm = g_plugins[idx];
+  }
+  CompiledModule cm;
+  std::string path;
+  int rc = compile_module(pm, &cm, &path);
+  if (rc) return rc;
+  if (cache_path && cache_path_cap > 0) std::snprintf(cache_path, static_cast<size_t>(cache_path_cap), "%s", path.c_str());
+  return 0;
+}
+
 // ---------------------------------------------------------------- problem
 int altro_b200_problem_create(int n, int m, int N, altro_b200_problem** out) {
   if (!out || n <= 0 || m <= 0 || N <= 0 || n > kMaxDim || m > kMaxDim)
@@ -694,6 +847,12 @@ void altro_b200_problem_destroy(altro_b200_problem* p) { delete p; }
 int altro_b200_problem_set_model(altro_b200_problem* p, int model, const double* params, int nparams) {
   if (!p || nparams < 0 || (nparams > 0 && !params)) return fail(ALTRO_B200_ERR_ARG, "set_model: bad argument");
   if (model == kCartpole && nparams != 4) return fail(ALTRO_B200_ERR_ARG, "cartpole needs params mc, mp, l, g");
+  if (model >= kFirstPluginId) {
+    std::lock_guard<std::mutex> lock(g_plugin_mutex);
+    const int idx = model - kFirstPluginId;
+    if (idx >= static_cast<int>(g_plugins.size())) return fail(ALTRO_B200_ERR_ARG, "set_model: unknown plug-in model id");
+    if (g_plugins[idx].nparams != nparams) return fail(ALTRO_B200_ERR_ARG, "set_model: the plug-in model takes " + std::to_string(g_plugins[idx].nparams) + " parameters");
+  }
   p->model = model;
   p->params.assign(params, params + nparams);
   p->model_set = true;
@@ -855,7 +1014,10 @@ int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_con
     }
   s->device = device;
   s->use_al = use_constraints != 0;
-  lookup_ops(p->n, p->m, p->model, s->W, &s->ops);
+  if ((rc = lookup_ops_rc(p->n, p->m, p->model, s->W, &s->ops))) {
+    if (g_err.empty() || rc == ALTRO_B200_ERR_UNSUPPORTED) return fail(rc, "no kernels for this model at tile width " + std::to_string(s->W));
+    return rc;  // the message of the module compiler / loader stands
+  }
   std::memset(&s->P, 0, sizeof(s->P));
   SolverParams& P = s->P;
   P.B = batch; P.T = s->T; P.N = p->N; P.W = s->W; P.Bp = s->Bp;

@@ -17,8 +17,15 @@
 // latency-bound serial sweeps are spread over 4x more warps; huge batches use W = 32.
 #pragma once
 
+#ifdef __CUDACC_RTC__
+// run-time compilation of a model module (NVRTC has no host headers): the few fixed-width names used below
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef long long int64_t;
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 namespace altro_b200 {
 

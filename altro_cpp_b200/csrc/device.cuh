@@ -55,7 +55,23 @@ __device__ __forceinline__ void mattmul(const double* A, const double* B, double
 }
 
 // ------------------------------------------------------------------------------------------
-// Continuous models.  eval(): xdot = f(x,u);  jac(): dense A (n x n), B (n x m) col-major.
+// Dynamics functors.  THE MODEL CONCEPT every kernel template is written against (and what a
+// plug-in supplied at run time has to provide — csrc/modules.inl, plugins/*.cuh):
+//
+//   struct Model {
+//     static constexpr int n, m;                       // state and control dimensions
+//     static constexpr bool kDiscrete;                 // false: continuous model, discretised by RK4 here
+//     static constexpr bool kStage3RepeatsStage2;      // true only if RK4 stages 2 and 3 provably coincide
+//     // xdot = f(x, u); P = the problem's model parameters (altro_b200_problem_set_model)
+//     static __device__ void eval(const double* P, const double* x, const double* u, double* xd);
+//     // dense Jacobians, column-major: A = df/dx (n x n), B = df/du (n x m); every entry written
+//     static __device__ void jac(const double* P, const double* x, const double* u, double* A, double* B);
+//     // optional: both at once when they share work
+//     static __device__ void eval_jac(const double* P, const double* x, const double* u, double* xd, double* A, double* B);
+//   };
+//
+// This is the device-side counterpart of the reference's ContinuousDynamics::Evaluate / Jacobian
+// (altro/problem/dynamics.hpp:59-99 there).  Everything is a compile-time-sized register array.
 // ------------------------------------------------------------------------------------------
 struct Unicycle {  // examples/unicycle.cpp:12-33
   static constexpr int n = 3, m = 2;
@@ -132,51 +148,6 @@ struct TripleIntegrator {  // examples/triple_integrator.cpp:9-33
       A[(i + dof) + (i + 2 * dof) * n] = 1.0;
       B[(i + 2 * dof) + i * n] = 1.0;
     }
-  }
-};
-
-struct Cartpole {  // definition owned by this repo; oracle: altro_oracle.hpp ModelEvaluate
-  static constexpr int n = 4, m = 1;
-  static constexpr bool kDiscrete = false;
-  static constexpr bool kStage3RepeatsStage2 = false;
-  static __device__ __forceinline__ void eval(const double* P, const double* x, const double* u,
-                                              double* xd) {
-    const double mc = P[0], mp = P[1], l = P[2], g = P[3];
-    const double thd = x[3];
-    double s, c;
-    sincos(x[1], &s, &c);
-    const double den = mc + mp * s * s;
-    const double F = u[0];
-    xd[0] = x[2];
-    xd[1] = thd;
-    xd[2] = (F + mp * s * (l * thd * thd + g * c)) / den;
-    xd[3] = (-F * c - mp * l * thd * thd * c * s - (mc + mp) * g * s) / (l * den);
-  }
-  static __device__ __forceinline__ void jac(const double* P, const double* x, const double* u,
-                                             double* A, double* B) {
-    const double mc = P[0], mp = P[1], l = P[2], g = P[3];
-    const double thd = x[3];
-    double s, c;
-    sincos(x[1], &s, &c);
-    const double den = mc + mp * s * s;
-    const double F = u[0];
-    const double numx = F + mp * s * (l * thd * thd + g * c);
-    const double numt = -F * c - mp * l * thd * thd * c * s - (mc + mp) * g * s;
-    const double dden = 2.0 * mp * s * c;
-    const double dnumx = mp * c * (l * thd * thd + g * c) - mp * s * g * s;
-    const double dnumt = F * s - mp * l * thd * thd * (c * c - s * s) - (mc + mp) * g * c;
-    ALTRO_UNROLL
-    for (int i = 0; i < 16; ++i) A[i] = 0.0;
-    A[0 + 2 * 4] = 1.0;
-    A[1 + 3 * 4] = 1.0;
-    A[2 + 1 * 4] = (dnumx * den - numx * dden) / (den * den);
-    A[2 + 3 * 4] = (2.0 * mp * s * l * thd) / den;
-    A[3 + 1 * 4] = (dnumt * den - numt * dden) / (l * den * den);
-    A[3 + 3 * 4] = (-2.0 * mp * l * thd * c * s) / (l * den);
-    B[0] = 0.0;
-    B[1] = 0.0;
-    B[2] = 1.0 / den;
-    B[3] = -c / (l * den);
   }
 };
 

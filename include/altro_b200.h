@@ -121,6 +121,23 @@ int altro_b200_problem_set_uniform_step(altro_b200_problem* p, float h);
 int altro_b200_problem_set_cost(altro_b200_problem* p, int k0, int k1, const double* Q,
                                 const double* R, const double* H, const double* q,
                                 const double* r, double c);
+/* ------------------------------------------------------------------------------------
+ * Plug-in dynamics models.  The reference is extended by subclassing
+ * ContinuousDynamics (altro/problem/dynamics.hpp:59-99) — host virtuals the device cannot call.
+ * Here a model is the CUDA source text of a functor struct (the concept is documented in
+ * altro_cpp_b200/csrc/device.cuh, an example is altro_cpp_b200/plugins/cartpole.cuh); the library
+ * instantiates its kernel templates on it with NVRTC when a solver for it is created, caches the
+ * module on disk, and from then on treats it like a built-in model (RK4-discretised).
+ *   name        the struct's name (a C++ identifier); registering the same (name, source) twice
+ *               returns the same id
+ *   *model_id   the id to pass to altro_b200_problem_set_model
+ * ---------------------------------------------------------------------------------- */
+int altro_b200_register_model(const char* name, const char* cuda_source, int n, int m, int nparams,
+                              int* model_id);
+/* compile the model's module into the on-disk cache now (NVRTC only: needs no GPU); cache_path
+ * (optional) receives the file name */
+int altro_b200_precompile_model(int model_id, char* cache_path, int cache_path_cap);
+
 /* SetConstraint(GoalConstraint(xf), k)  — Equality; examples/basic_constraints.hpp:15-40 */
 int altro_b200_problem_add_goal(altro_b200_problem* p, int k, const double* xf);
 /* SetConstraint(ControlBound(lb,ub), k) — Inequality; examples/basic_constraints.hpp:42-150.

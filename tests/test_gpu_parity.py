@@ -271,7 +271,7 @@ def test_solve_unicycle_turn90_ilqr(gpu, oracle):
     assert frac == 0.0
     for k in ("X", "U", "cost"):
         assert errs[k] <= RTOL, errs
-    assert errs["K"] <= 1e-7 and errs["d"] <= 1e-6, errs
+    assert errs["K"] <= 1e-6 and errs["d"] <= 1e-6, errs
 
 
 def test_solve_unicycle_turn90_al(gpu, oracle):
@@ -294,7 +294,7 @@ def test_solve_unicycle_three_obstacles_al(gpu, oracle):
     assert frac == 0.0
     assert errs["X"] <= 1e-9 and errs["cost"] <= 1e-9, errs
     assert errs["U"] <= 1e-8, errs   # instances that run 160+ iterations (module docstring)
-    assert errs["K"] <= 1e-7 and errs["d"] <= 1e-6, errs
+    assert errs["K"] <= 1e-6 and errs["d"] <= 1e-6, errs
     assert np.array_equal(r["status"], ref["status"])
 
 
