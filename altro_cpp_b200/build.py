@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libaltro_b200.so")
-SOURCES = ["altro_b200.cu", "altro_b200_large.cu"]
+SOURCES = ["altro_b200.cu", "altro_b200_large.cu", "altro_b200_large_mma.cu"]
 # per-source extra flags: the large-state path is compiled without FMA contraction (bit parity)
 EXTRA = {"altro_b200_large.cu": ["-fmad=false"]}
 

@@ -33,6 +33,8 @@
 // large-state path, compiled in its own translation unit (altro_b200_large.cu) without FMA
 // contraction so that its ill-conditioned LLT decisions match the CPU oracle bit for bit
 cudaError_t altro_b200_launch_solve_large_32_8(const altro_b200::SolverParams& P, int mode, cudaStream_t st);
+// the same path on the fp64 tensor instruction, one instance per warp (altro_b200_large_mma.cu)
+cudaError_t altro_b200_launch_solve_large_mma_32_8(const altro_b200::SolverParams& P, int mode, int sm_count, cudaStream_t st);
 
 using namespace altro_b200;
 
@@ -426,12 +428,25 @@ Ops make_ops() {
 
 #include "modules.inl"
 
+int default_engine();
+
+// Large-state path: engine "fused" = the exact-order kernel, one instance per CTA (large.cuh, bit-equal to
+// the oracle); otherwise the tensor-instruction kernel, one instance per warp (large_mma.cuh, equal to rounding).
 Ops make_large_ops_32_8() {
   Ops o;
   o.large = true;
-  o.solve = [](const SolverParams& P, int mode, int, int, cudaStream_t st) -> cudaError_t {
-    return altro_b200_launch_solve_large_32_8(P, mode, st);
-  };
+  if (default_engine() == ALTRO_B200_ENGINE_FUSED) {
+    o.solve = [](const SolverParams& P, int mode, int, int, cudaStream_t st) -> cudaError_t {
+      return altro_b200_launch_solve_large_32_8(P, mode, st);
+    };
+  } else {
+    o.solve = [](const SolverParams& P, int mode, int, int, cudaStream_t st) -> cudaError_t {
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      return altro_b200_launch_solve_large_mma_32_8(P, mode, sms, st);
+    };
+  }
   return o;
 }
 
@@ -996,9 +1011,9 @@ int altro_b200_solver_create(const altro_b200_problem* p, int batch, int use_con
     return fail(ALTRO_B200_ERR_UNSUPPORTED, "the large-state path (n=32) supports unconstrained problems only");
   if (probe.large && static_cast<int>(p->params.size()) != p->n * (p->n + p->m))
     return fail(ALTRO_B200_ERR_ARG, "linear model needs params = [A (n*n), B (n*m)]");
-  s->engine = probe.large ? ALTRO_B200_ENGINE_FUSED : default_engine();
+  s->engine = default_engine();
   s->W = probe.large ? 1 : choose_tile_width(batch, sm_count);
-  if (s->engine == ALTRO_B200_ENGINE_PHASED) {
+  if (s->engine == ALTRO_B200_ENGINE_PHASED && !probe.large) {
     if (std::getenv("ALTRO_B200_TILE") && s->W != kPhasedTile) s->engine = ALTRO_B200_ENGINE_FUSED;
     else s->W = kPhasedTile;
   }

@@ -538,23 +538,61 @@ def test_solve_triple_integrator_full_c3_slice(gpu, oracle):
 
 @pytest.mark.parametrize("literal", [False, True])
 def test_solve_random_lqr_c5(gpu, oracle, literal):
-    # BASELINE config C5: n = 32, m = 8, N = 100, unconstrained (one instance per CTA, large.cuh,
-    # compiled without FMA contraction and summing in the oracle's order -> expected bit-equal).
-    # The model is not in the reference: parity is GPU vs oracle only.  literal=True is the
-    # ill-conditioned variant whose LLT decisions hinge on the last bit (problems.py).
+    # BASELINE config C5: n = 32, m = 8, N = 100, unconstrained.  The model is not in the reference: parity
+    # is GPU vs oracle only.  Two kernels, selected by the engine:
+    #   fused  -> large.cuh, one instance per CTA, no FMA contraction, sums in the oracle's order: bit-equal;
+    #   phased -> large_mma.cuh (the default), one instance per warp on mma.sync.m8n8k4.f64: equal to rounding.
+    # literal=True is the ill-conditioned variant whose LLT decisions hinge on the last bit (problems.py):
+    # there the tensor kernel may leave the oracle's discrete path; the fraction is printed and the
+    # result must still be the same minimiser.
     spec = P.random_lqr_problem(literal=literal)
     X0 = P.normal_initial_states(spec, 24 if literal else 48)
-    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, al=True, max_mismatch_frac=0.0)
+    exact = gpu._test_engine == "fused"
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, al=True,
+                                       max_mismatch_frac=0.0 if (exact or not literal) else 1.0)
     assert np.all(r["status"] == 0)
     if not literal:
         assert np.all(r["iters"][:, 0] == 2)
-    for k in ("X", "U", "cost", "K", "d"):
-        assert errs[k] <= 1e-12, errs
+    if exact:
+        for k in ("X", "U", "cost", "K", "d"):
+            assert errs[k] <= 1e-12, errs
+    elif not literal:
+        print("[parity] C5 tensor kernel vs oracle:", {k: f"{v:.2e}" for k, v in errs.items()})
+        for k in ("X", "U", "cost", "K", "d"):
+            assert errs[k] <= 1e-9, errs
+    else:
+        cost_err = np.abs(r["cost"] - ref["cost"]) / np.maximum(1.0, np.abs(ref["cost"]))
+        print(f"[parity] C5 literal, tensor kernel: {frac:.3f} off the oracle's discrete path, cost err {cost_err.max():.2e}")
+        assert cost_err.max() <= 1e-6
     # step-wise methods are not offered on this path
     s = gpu.BatchSolver(spec, 4)
     s.set_inputs(X0[:4])
     with pytest.raises(gpu.SolverError, match="not available on the large-state path"):
         s.rollout()
+
+
+def test_large_state_kernels_agree_on_a_ragged_batch(gpu):
+    """The tensor kernel (one instance per warp, 8 per CTA, instances dealt round-robin over the SMs)
+    against the exact-order kernel on a batch that does not fill the last round: same status and
+    iteration counts, X / U / cost / K / d equal to rounding."""
+    if gpu._test_engine != "phased":
+        pytest.skip("once")
+    spec = P.random_lqr_problem()
+    B = 1500   # 148 SMs x 8 warps = 1184 per round: one full round and a ragged one
+    X0 = P.normal_initial_states(spec, B)
+    out = {}
+    for eng in ("fused", "phased"):
+        gpu.set_default_engine(eng)
+        s = gpu.BatchSolver(spec, B)
+        s.set_inputs(X0); s.solve_al()
+        r = s.results(); X, U = s.trajectory(); K, d = s.gains()
+        out[eng] = dict(status=r["status"], iters=r["iters"], cost=r["cost"], X=X, U=U, K=K, d=d)
+    gpu.set_default_engine("phased")
+    a, b = out["fused"], out["phased"]
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iters"], b["iters"])
+    for k in ("X", "U", "cost", "K", "d"):
+        e = np.abs(a[k] - b[k]).max() / max(1.0, np.abs(a[k]).max())
+        assert e <= 1e-10, (k, e)
 
 
 def test_warm_start_resolve_keeps_duals_and_penalties(gpu, oracle):
