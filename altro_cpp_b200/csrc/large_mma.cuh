@@ -171,6 +171,11 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_large_mma(SolverParams
       bool ok = true;
       const double* Zc = zptr(zsel, 0);
       double* Zn = zptr(closed ? zout : zsel, 0);
+      double arow[n], brow[m];
+#pragma unroll
+      for (int j = 0; j < n; ++j) arow[j] = As[lane + j * kLdW];
+#pragma unroll
+      for (int j = 0; j < m; ++j) brow[j] = Bs[lane + j * kLdW];
       const double* KDb = kdptr(0);
       // the next knot's reference point and gains are requested one knot ahead (HBM latency off the chain)
       double zx_n = Zc[lane], zu_n = lane < m ? Zc[n + lane] : 0.0, kq_n[8], dq_n = 0.0;
@@ -198,9 +203,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_large_mma(SolverParams
         if (k < N && closed) {
           vdx[lane] = x - zx;
           __syncwarp();
-          double acc = 0.0;  // lane l: row l % 8 of K, columns l / 8 + 4 t
+          double acc = 0.0, acc1 = 0.0;  // lane l: row l % 8 of K, columns l / 8 + 4 t
 #pragma unroll
-          for (int t = 0; t < 8; ++t) acc = fma(kq[t], vdx[(lane >> 3) + 4 * t], acc);
+          for (int t = 0; t < 8; t += 2) {
+            acc = fma(kq[t], vdx[(lane >> 3) + 4 * t], acc);
+            acc1 = fma(kq[t + 1], vdx[(lane >> 3) + 4 * t + 4], acc1);
+          }
+          acc += acc1;
           acc += __shfl_xor_sync(0xffffffffu, acc, 8);
           acc += __shfl_xor_sync(0xffffffffu, acc, 16);
           double ratio = 0.0;
@@ -221,16 +230,21 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_solve_large_mma(SolverParams
         if (closed && lane < m) zn[n + lane] = u;
         Jl += knot_cost_lane(k, x, u);
         if (k < N) {  // x+ = A x + B u
-          double a0 = 0.0, a1 = 0.0;
-#pragma unroll 8
-          for (int j = 0; j < n; j += 2) {
-            a0 = fma(As[lane + j * kLdW], vx[j], a0);
-            a1 = fma(As[lane + (j + 1) * kLdW], vx[j + 1], a1);
-          }
-          double bu = 0.0;
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;  // row `lane` of A and B sits in registers for the whole sweep
 #pragma unroll
-          for (int j = 0; j < m; ++j) bu = fma(Bs[lane + j * kLdW], vu[j], bu);
-          x = (a0 + a1) + bu;
+          for (int j = 0; j < n; j += 4) {
+            a0 = fma(arow[j], vx[j], a0);
+            a1 = fma(arow[j + 1], vx[j + 1], a1);
+            a2 = fma(arow[j + 2], vx[j + 2], a2);
+            a3 = fma(arow[j + 3], vx[j + 3], a3);
+          }
+          double b0 = 0.0, b1 = 0.0;
+#pragma unroll
+          for (int j = 0; j < m; j += 2) {
+            b0 = fma(brow[j], vu[j], b0);
+            b1 = fma(brow[j + 1], vu[j + 1], b1);
+          }
+          x = ((a0 + a1) + (a2 + a3)) + (b0 + b1);
           if (closed && o.check_forwardpass_bounds) {  // ilqr.hpp:484-495 (sqrt(s) > max <=> s > max_sq)
             // |x|^2 > t needs some x_i^2 > t / n (n + 1 below: slack for the rounding of the sum): one vote rules
             // the norms out on almost every knot

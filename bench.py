@@ -281,6 +281,28 @@ def strong_scaling_c3(pkg, torch, dist, world, rank, dev, local_rank, stream, st
     return out
 
 
+FP64_TENSOR_PEAK_TFLOPS = 37.1  # profiles/r02_dmma_rate.txt: mma.sync.m8n8k4.f64, 148 SMs x 8 warps x 4 chains
+
+
+def c5_roofline(n, m, N, backward_passes, ms_step, engine):
+    """Large-state path: the whole solve is ONE kernel (large_mma.cuh), bound by the fp64 tensor pipe.
+    Algorithmic flops of one Riccati step (CalcActionValueExpansion + CalcCostToGo as dense products,
+    DESIGN.md section 7): A'P, (A'P)A: 2 n^3 each; B'P, (B'P)A: 2 m n^2 each; (B'P)B, Quu K: 2 m^2 n each;
+    K'(Quu K + Qux), Qxu K: 2 m n^2 each.  achieved = those flops x knot points x backward passes of the
+    step / the step's duration (the step is that one kernel plus ~10 us of host-side launches)."""
+    step_flops = 2.0 * (2 * n ** 3 + 4 * m * n * n + 2 * m * m * n)
+    flops = step_flops * N * backward_passes
+    achieved = flops / (ms_step * 1e-3) / 1e12
+    return {"kernel": "k_solve_large_mma — whole AL-iLQR solves, one instance per warp, dense products on "
+                      "mma.sync.m8n8k4.f64" if engine == "phased" else "k_solve_large — exact-order kernel, one instance per CTA",
+            "bound": "tensor", "achieved": achieved, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+            "frac": achieved / FP64_TENSOR_PEAK_TFLOPS,
+            "peak_source": "measured fp64 mma.sync rate on this pool's B200 (tools/micro/dmma_rate.cu, "
+                           "profiles/r02_dmma_rate.txt); MEASURED_PEAKS.json has no fp64 entry",
+            "traffic": None, "flops_per_launch": flops, "ms_per_launch": ms_step,
+            "flops_per_riccati_step": step_flops}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -568,7 +590,8 @@ def main():
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": None if not have_bp else {
+            "roofline": c5_roofline(n, m, N, float(stats[1].item()) / world, ms, solver.engine) if args.workload.startswith("c5")
+            else None if not have_bp else {
                 "kernel": "k_backward_mat<phased> — the backward pass as a solve launches it (TMA-streamed "
                           "materialised expansions), full batch",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -583,7 +606,10 @@ def main():
                              "kernels": ("k_outer_* (dense list, every 2nd slot) -> k_update_expansions -> "
                                          "k_backward_mat(TMA) -> k_ls_wide -> k_ls_deep (k_roll/k_cost/k_acc when few "
                                          "instances remain)")
-                             if solver.engine == "phased" else "k_solve (fused persistent AL-iLQR)",
+                             if solver.engine == "phased" and not args.workload.startswith("c5")
+                             else ("k_solve_large_mma (whole solves, one instance per warp)" if solver.engine == "phased"
+                                   else "k_solve_large (whole solves, one instance per CTA, exact order)")
+                             if args.workload.startswith("c5") else "k_solve (fused persistent AL-iLQR)",
                              "backward_passes_per_step": float(stats[1].item()),
                              "contract_GBps": float(stats[1].item()) * (bp_bytes / B) / (ms * 1e-3) / 1e9},
             "extras": extras,
