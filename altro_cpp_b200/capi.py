@@ -300,6 +300,24 @@ class BatchSolver:
         self._call("get_scalars_host", *[_p(arrs[k]) for k in names], _stream_ptr(stream))
         return arrs
 
+    # ---- per-iteration statistics (SolverStats vectors, altro/common/solver_stats.hpp:54-61) ----
+    HISTORY_COLS = ("cost", "alpha", "z", "gradient", "cost_decrease", "regularization", "violations", "max_penalty")
+
+    def enable_history(self, instances: int = 1, rows: int = 1000):
+        """Record one row per inner iteration for the first `instances` instances (call before solving;
+        a recording solver runs on the fused engine)."""
+        self._call("solver_enable_history", ctypes.c_int(int(instances)), ctypes.c_int(int(rows)))
+        self._hist_rows = int(rows)
+
+    def history(self, instance: int = 0, stream=None):
+        """-> dict name -> array[iterations]: the value each SolverStats vector holds in the row that
+        iteration wrote (carry-forward included)."""
+        rows = np.zeros((self._hist_rows, len(self.HISTORY_COLS)))
+        n = ctypes.c_int(0)
+        self._call("get_history_host", ctypes.c_int(int(instance)), _p(rows), ctypes.c_int(self._hist_rows),
+                   ctypes.byref(n), _stream_ptr(stream))
+        return {k: rows[:n.value, i].copy() for i, k in enumerate(self.HISTORY_COLS)}
+
     # ---- measurement ------------------------------------------------------------------
     def backward_pass_bytes(self) -> int: return int(lib().altro_b200_backward_pass_bytes(self._h))
     def kernel_launches(self) -> int: return int(lib().altro_b200_kernel_launches(self._h))

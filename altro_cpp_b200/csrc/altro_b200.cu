@@ -596,6 +596,7 @@ struct altro_b200_solver {
   } sec[2];
   int* d_list = nullptr;
   int* h_count = nullptr;  // pinned
+  int hist_instances = 0, hist_rows = 0;  // per-iteration SolverStats rows recorded for the first instances
 
   int alloc(void** p, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes);
@@ -1229,8 +1230,9 @@ static int solve_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
   if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
   if (!s->inputs_set) return fail(ALTRO_B200_ERR_STATE, "Initial state must be set before solving.");
   DeviceGuard guard(s->device);
-  const int budget = std::max(1, env_int("ALTRO_B200_BUDGET", 16));
-  const int repack_pct = env_int("ALTRO_B200_REPACK_PCT", 100);  // 0 disables re-packing
+  // a solver that records history keeps part of its bookkeeping in registers: it solves in one launch
+  const int budget = s->P.HIST ? (1 << 30) : std::max(1, env_int("ALTRO_B200_BUDGET", 16));
+  const int repack_pct = s->P.HIST ? 0 : env_int("ALTRO_B200_REPACK_PCT", 100);  // 0 disables re-packing
   int rc;
   if ((rc = fill_int(s, I_PHASE, mode == 1 ? kPhAlInit : kPhSolveStart, st))) return rc;
   if ((rc = fill_int(s, I_LSFAIL, 0, st))) return rc;
@@ -1779,6 +1781,42 @@ size_t altro_b200_backward_pass_bytes(const altro_b200_solver* s) {
   return per * s->B;
 }
 int64_t altro_b200_kernel_launches(const altro_b200_solver* s) { return s ? s->launches : 0; }
+
+int altro_b200_solver_enable_history(altro_b200_solver* s, int instances, int rows) {
+  if (!s) return fail(ALTRO_B200_ERR_ARG, "null solver");
+  if (s->ops.large) return fail(ALTRO_B200_ERR_UNSUPPORTED, "history is not recorded on the large-state path");
+  if (instances <= 0 || rows <= 0) return fail(ALTRO_B200_ERR_ARG, "enable_history: instances and rows must be positive");
+  if (s->P.HIST) return fail(ALTRO_B200_ERR_STATE, "enable_history: already enabled");
+  DeviceGuard guard(s->device);
+  instances = std::min(instances, s->B);
+  void* p = nullptr;
+  int rc = s->alloc_zeroed(&p, static_cast<size_t>(instances) * rows * kHistCols * sizeof(double));
+  if (rc) return rc;
+  s->P.HIST = static_cast<double*>(p);
+  s->P.hist_instances = s->hist_instances = instances;
+  s->P.hist_rows = s->hist_rows = rows;
+  s->engine = ALTRO_B200_ENGINE_FUSED;  // the rows are written by k_solve
+  return 0;
+}
+
+int altro_b200_get_history_host(altro_b200_solver* s, int instance, double* rows_out, int max_rows, int* nrows,
+                                void* stream) {
+  if (!s || !rows_out || !nrows) return fail(ALTRO_B200_ERR_ARG, "get_history: null argument");
+  if (!s->P.HIST) return fail(ALTRO_B200_ERR_STATE, "get_history: altro_b200_solver_enable_history was not called");
+  if (instance < 0 || instance >= s->hist_instances) return fail(ALTRO_B200_ERR_ARG, "get_history: instance not recorded");
+  DeviceGuard guard(s->device);
+  int it_total = 0;
+  CU(cudaMemcpyAsync(&it_total, s->P.is + static_cast<size_t>(I_ITERS_TOTAL) * s->Bp + instance, sizeof(int),
+                     cudaMemcpyDeviceToHost, S(stream)));
+  CU(cudaStreamSynchronize(S(stream)));
+  const int n = std::max(0, std::min(std::min(it_total, s->hist_rows), max_rows));
+  if (n > 0)
+    CU(cudaMemcpyAsync(rows_out, s->P.HIST + static_cast<size_t>(instance) * s->hist_rows * kHistCols,
+                       static_cast<size_t>(n) * kHistCols * sizeof(double), cudaMemcpyDeviceToHost, S(stream)));
+  CU(cudaStreamSynchronize(S(stream)));
+  *nrows = n;
+  return 0;
+}
 size_t altro_b200_device_bytes(const altro_b200_solver* s) { return s ? s->dev_bytes : 0; }
 
 }  // extern "C"

@@ -235,8 +235,14 @@ struct SolverParams {
                   //                also [entry][N+1] per-knot costs of the outer-step kernels
   int* TRYST;     // [rows][32]     phased engine: status left by each candidate rollout
   int split_cap;  // list entries CAND / COSTK / TRYST have room for in the split deep kernels
+  double* HIST;   // [hist_instances][hist_rows][kHistCols] per-iteration SolverStats rows (nullptr: not recorded)
+  int hist_instances, hist_rows;
   DevOptions opt;
 };
+
+// Columns of one history row = the double-valued SolverStats vectors (altro/common/solver_stats.hpp:54-61).
+enum HistCol : int { kHistCost = 0, kHistAlpha, kHistZ, kHistGradient, kHistCostDecrease, kHistRegularization,
+                     kHistViolations, kHistMaxPenalty, kHistCols };
 
 __host__ __device__ inline int exp_fields(int n, int m) {
   return n * (n + m) + n * n + n * m + m * m + n + m;

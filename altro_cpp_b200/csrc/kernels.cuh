@@ -311,7 +311,7 @@ template <class M, int W, bool kStoreCtg>
 __device__ __forceinline__ void sweep_backward(const Lane<M, W>& L, double* stg, bool active,
                                                int zsel, double penalty, double& reg,
                                                double& dreg, double& dV0, double& dV1,
-                                               int& status, double& gsum) {
+                                               int& status, double& gsum, double* reg_log = nullptr) {
   constexpr int n = M::n, m = M::m, nz = n + m, G = Lane<M, W>::G;
   const int N = L.P.N, pmax = L.P.pmax;
   const DevOptions& o = L.P.opt;
@@ -446,7 +446,8 @@ __device__ __forceinline__ void sweep_backward(const Lane<M, W>& L, double* stg,
   }
   if (active && lead) {
     gsum = gs;
-    decrease_reg(o, reg, dreg);  // ilqr.hpp:443-444
+    if (reg_log) *reg_log = reg;  // stats.Log("reg", rho_) precedes the decrease, ilqr.hpp:442
+    decrease_reg(o, reg, dreg);   // ilqr.hpp:443-444
   }
 }
 
@@ -719,6 +720,10 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
     lsfail = L.is(I_LSFAIL);
   }
   const bool was_reported = phase >= kPhReported;
+  // history rows (P.HIST): the value stats.max_penalty carries into the rows of the current iLQR solve — logged by
+  // Init() and after every dual update, BEFORE UpdatePenalties (al_solver.hpp:298, 362).  Lives in a register: a
+  // solver that records history solves in one launch (altro_b200.cu).
+  double pen_logged = 0.0;
   if (phase == kPhAlInit) {  // AugmentedLagrangianiLQR::Init, al_solver.hpp:287-302 (Q10)
     if (o.reset_duals && has_con && L.a == 0) {
       for (int k = 0; k <= N; ++k) {
@@ -733,6 +738,7 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
     cost_prev = 0.0;
     st_al = kUnsolved;
     phase = kPhSolveStart;
+    pen_logged = has_con ? penalty : 0.0;
   }
   __syncwarp();
 
@@ -759,6 +765,7 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
         viol = v;
         it_outer++;
         const double max_penalty = has_con ? penalty : 0.0;
+        pen_logged = max_penalty;
         phase = kPhDone;  // IsDone, al_solver.hpp:368-401 (Q16)
         if (st != kSolved) {
           st_al = st;
@@ -805,7 +812,8 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
       double gs_bwd = 0.0;
       if (run) csrc = -1.0;  // UpdateExpansions evaluates every constraint at Z_
       const double reg_in = reg, dreg_in = dreg;
-      sweep_backward<M, W, false>(L, stg, run, zsel, penalty, reg, dreg, dV0, dV1, st, gs_bwd);
+      double reg_logged = reg;
+      sweep_backward<M, W, false>(L, stg, run, zsel, penalty, reg, dreg, dV0, dV1, st, gs_bwd, &reg_logged);
       reg = __shfl_sync(kFull, reg, L.i);
       dreg = __shfl_sync(kFull, dreg, L.i);
       dV0 = __shfl_sync(kFull, dV0, L.i);
@@ -826,6 +834,34 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp, (W <= 4 ? ALTRO_SOLVE_MINB
         t.dreg_in = dreg_in;
         finish_inner(o, N, mode, t, zsel, J0, cost_cur, cost_prev, initial_cost, alpha_stat, z_stat, csrc,
                      grad, dJ, reg, dreg, it_inner, it_total, st, phase, lsfail);
+      }
+      if (P.HIST != nullptr) {
+        // One SolverStats row per inner iteration (UpdateConvergenceStatistics, ilqr.hpp:568-587).  "violations" is
+        // MaxViolationStored(): of the accepted trajectory, or — after a fully failed search — of the last
+        // candidate evaluated (Q8), which is regenerated here exactly like the dual update regenerates it.
+        const bool rejected = run && csrc >= 0.0;
+        double vs = 0.0, vr = 0.0;
+        if (__any_sync(kFull, run && !rejected))
+          sweep_cost<M, W, false>(L, stg, run && !rejected && L.a == 0, zsel, penalty, &vs);
+        if (__any_sync(kFull, rejected)) {
+          double Jt, gt;
+          int stt = st;
+          sweep_forward<M, W, true>(L, stg, rejected && L.a == 0, zsel, Lane<M, W>::cand(zsel, 0), csrc, penalty,
+                                    Jt, gt, &vr, stt);
+          __syncwarp();
+        }
+        const int orig = valid ? L.is(I_ORIG) : 0;
+        if (run && lead && orig < P.hist_instances && it_total >= 1 && it_total <= P.hist_rows) {
+          double* h = P.HIST + (static_cast<size_t>(orig) * P.hist_rows + (it_total - 1)) * kHistCols;
+          h[kHistCost] = cost_cur;
+          h[kHistAlpha] = alpha_stat;
+          h[kHistZ] = z_stat;
+          h[kHistGradient] = grad;
+          h[kHistCostDecrease] = dJ;
+          h[kHistRegularization] = reg_logged;
+          h[kHistViolations] = rejected ? vr : vs;
+          h[kHistMaxPenalty] = pen_logged;
+        }
       }
     }
   }

@@ -316,8 +316,39 @@ class DeviceSolver {
       throw;
     }
   }
-  // per-iteration history of instance 0 into SolverStats (filled when the device recorded one)
-  void PullHistory() {}
+  // step-wise use (ForwardPass / UpdateConvergenceStatistics called one by one): the scalars the reference logs
+  struct StepScalars { double alpha, z, dJ, grad; };
+  StepScalars Scalars(int b = 0) {
+    Need();
+    std::vector<double> a(B_), z(B_), dj(B_), g(B_);
+    Check(altro_b200_get_scalars_host(solver_, nullptr, nullptr, nullptr, a.data(), z.data(), dj.data(), g.data(), nullptr,
+                                      nullptr, nullptr),
+          "GetStats");
+    return {a[b], z[b], dj[b], g[b]};
+  }
+  // Per-iteration SolverStats vectors (cost, alpha, improvement_ratio, gradient, cost_decrease, regularization,
+  // violations, max_penalty) of a single-problem solver, rebuilt from the rows the device recorded: one row per
+  // inner iteration plus the open slot NewIteration() leaves behind (solver_stats.cpp:54-66), into which the
+  // AL solver logs the final violation and penalty (al_solver.hpp:361-362).  `al`: called by the AL solver.
+  void PullHistory(bool al = true) {
+    if (!history_ || Sharded() || !solver_) return;
+    const int cap = history_rows_;
+    std::vector<double> rows(static_cast<size_t>(cap) * ALTRO_B200_HISTORY_COLS);
+    int nrows = 0;
+    Check(altro_b200_get_history_host(solver_, 0, rows.data(), cap, &nrows, nullptr), "GetStats");
+    std::vector<double> col[ALTRO_B200_HISTORY_COLS];
+    for (int c = 0; c < ALTRO_B200_HISTORY_COLS; ++c) {
+      col[c].resize(nrows + 1);
+      for (int r = 0; r < nrows; ++r) col[c][r] = rows[static_cast<size_t>(r) * ALTRO_B200_HISTORY_COLS + c];
+      col[c][nrows] = nrows > 0 ? col[c][nrows - 1] : 0.0;  // NewIteration(): the new slot starts as a copy
+    }
+    if (al) {
+      col[6][nrows] = res_.viol.empty() ? 0.0 : res_.viol[0];
+      col[7][nrows] = has_constraints_ ? MaxPenalty(0) : 0.0;
+    }
+    stats_.SetHistory(nrows + 1, col[0].data(), col[1].data(), col[2].data(), col[3].data(), col[4].data(),
+                      col[5].data(), col[6].data(), col[7].data());
+  }
   const problem::Problem& GetProblem() const { return prob_; }
   int64_t KernelLaunches() const { return solver_ ? altro_b200_kernel_launches(solver_) : 0; }
 
@@ -391,10 +422,13 @@ class DeviceSolver {
       Check(altro_b200_problem_set_cost(p, k, k + 1, c.Q.data(), c.R.data(), c.H.data(), c.q.data(), c.r.data(), c.c),
             "SetCostFunction");
     }
+    has_constraints_ = false;
     if (use_constraints_) {
       for (int k = 0; k <= N_; ++k) {
         for (const auto& con : prob_.GetEqualityConstraints()[k]) AddConstraint(p, k, *con);
         for (const auto& con : prob_.GetInequalityConstraints()[k]) AddConstraint(p, k, *con);
+        has_constraints_ = has_constraints_ || !prob_.GetEqualityConstraints()[k].empty() ||
+                           !prob_.GetInequalityConstraints()[k].empty();
       }
     }
     Check(altro_b200_problem_set_initial_state(p, prob_.GetInitialState().data()), "SetInitialState");
@@ -404,6 +438,12 @@ class DeviceSolver {
       return;
     }
     Check(altro_b200_solver_create(p, B_, use_constraints_ ? 1 : 0, device_, &solver_), "solver");
+    if (B_ == 1) {  // the single-problem API keeps the reference's per-iteration SolverStats vectors
+      history_rows_ = std::max(1000, stats_.GetOptions().max_iterations_total);
+      const int rc = altro_b200_solver_enable_history(solver_, 1, history_rows_);
+      if (rc != ALTRO_B200_ERR_UNSUPPORTED) Check(rc, "GetStats");  // (not recorded on the large-state path)
+      history_ = rc == 0;
+    }
     if (have_penalty_) Check(altro_b200_solver_set_penalty(solver_, penalty_, nullptr), "SetPenalty");
   }
   template <class Con>
@@ -432,6 +472,8 @@ class DeviceSolver {
   problem::Problem prob_;  // shares the functors and the initial-state pointer with the caller
   int n_, m_, N_, B_, device_;
   bool use_constraints_;
+  bool has_constraints_ = false, history_ = false;
+  int history_rows_ = 0;
   altro_b200_solver* solver_ = nullptr;
   std::vector<int> devices_;
   altro_b200_multi* multi_ = nullptr;

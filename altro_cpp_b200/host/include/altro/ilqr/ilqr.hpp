@@ -130,7 +130,7 @@ class iLQR {
     Core().Run(detail::DeviceSolver::kSolveILQR);
     Core().Download(Z_.get());
     Core().Pull();
-    Core().PullHistory();
+    Core().PullHistory(/*al=*/false);
   }
   void Rollout() {
     Require();
@@ -161,10 +161,17 @@ class iLQR {
     Require();
     Core().Run(detail::DeviceSolver::kForwardPass);
     Core().Download(Z_.get());
+    const auto sc = Core().Scalars();  // stats_.Log("alpha" / "z"), ilqr.hpp:545-547 (carry-forward when the search failed)
+    GetStats().Log("alpha", sc.alpha);
+    GetStats().Log("z", sc.z);
   }
   void UpdateConvergenceStatistics() {
     Core().Run(detail::DeviceSolver::kUpdateConvergenceStatistics);
     Core().Pull();
+    const auto sc = Core().Scalars();  // ilqr.hpp:578-584
+    GetStats().Log("dJ", sc.dJ);
+    GetStats().Log("grad", sc.grad);
+    GetStats().NewIteration();
   }
   void SolveSetup() {
     SyncThreadBookkeeping();

@@ -302,6 +302,20 @@ int altro_b200_multi_last_timings(const altro_b200_multi* m, double* scatter_ms,
 size_t altro_b200_backward_pass_bytes(const altro_b200_solver* s);
 /* number of kernels this library has launched on behalf of `s` since creation */
 int64_t altro_b200_kernel_launches(const altro_b200_solver* s);
+
+/* ------------------------------------------------------------------------------------
+ * Per-iteration statistics  (replaces the vectors of SolverStats: cost, alpha, improvement_ratio,
+ * gradient, cost_decrease, regularization, violations, max_penalty — altro/common/solver_stats.hpp:54-61,
+ * filled by Log() in ilqr.hpp:442, 545-547, 578-584 and al_solver.hpp:298-299, 361-362)
+ * ---------------------------------------------------------------------------------- */
+/* Record one row per inner iteration for the first `instances` instances, at most `rows` rows each.
+ * Call before solving.  A recording solver runs on the fused engine (same results). */
+int altro_b200_solver_enable_history(altro_b200_solver* s, int instances, int rows);
+#define ALTRO_B200_HISTORY_COLS 8 /* cost, alpha, z, gradient, cost_decrease, regularization, violations, max_penalty */
+/* rows_out[r * 8 + c] = value column c holds in the SolverStats row that iteration r + 1 wrote
+ * (carry-forward included); *nrows = iterations recorded (<= max_rows). */
+int altro_b200_get_history_host(altro_b200_solver* s, int instance, double* rows_out, int max_rows,
+                                int* nrows, void* stream);
 /* latency probe: cycles per call of the per-knot device functions on one warp (cycles[32]) */
 int altro_b200_microbench(altro_b200_solver* s, long long* cycles, int reps);
 /* device bytes held by the solver */

@@ -215,6 +215,12 @@ void TestUnicycleILQR() {
   solver.ForwardPass();
   EXPECT(solver.Cost() < J0);
 
+  // unicycle_ilqr_test.cpp:56-65: the first line search accepts alpha = 1/16, logged in row 0 of the stats
+  EXPECT(solver.GetStats().alpha.size() == 1 && solver.GetStats().alpha[0] == 0.0625);
+  solver.UpdateConvergenceStatistics();
+  EXPECT(solver.GetStats().iterations_inner == 1 && solver.GetStats().cost_decrease.size() == 2);
+  EXPECT(solver.GetStats().cost_decrease[0] > 0.0 && solver.GetStats().gradient[0] > 0.0);
+
   // unicycle_ilqr_test.cpp:40-54: cost-to-go gradient and feedforward gain at knot 0
   auto step = def.MakeSolver();
   step.UpdateExpansions();
@@ -249,6 +255,17 @@ void TestUnicycleILQR() {
   EXPECT(fresh.GetStatus() == SolverStatus::kSolved);
   EXPECT(fresh.GetStats().iterations_inner == 9);
   EXPECT(std::fabs(fresh.Cost() - 0.0387016567) < 1e-5);
+  {  // unicycle_ilqr_test.cpp:96-99 and solver_stats.hpp:54-61: one row per iteration + the open slot
+    const altro::SolverStats& st = fresh.GetStats();
+    EXPECT(st.cost.size() == 10 && st.alpha.size() == 10 && st.gradient.size() == 10 && st.regularization.size() == 10);
+    EXPECT(st.alpha[0] == 0.0625);
+    EXPECT(st.cost_decrease.back() < fresh.GetOptions().cost_tolerance);
+    EXPECT(st.gradient.back() < fresh.GetOptions().gradient_tolerance);
+    EXPECT(std::fabs(st.cost[8] - 0.0387016567) < 1e-5 && st.cost[9] == st.cost[8]);
+    for (int i = 1; i < 9; ++i) EXPECT(st.cost[i] <= st.cost[i - 1]);
+    EXPECT(std::fabs(st.initial_cost - 259.27636137767087) < 1e-5);
+    EXPECT(std::fabs((st.initial_cost - st.cost[0]) - st.cost_decrease[0]) < 1e-9 * st.initial_cost);
+  }
   const altro::VectorXd& xN = fresh.GetTrajectory()->State(def.N);
   EXPECT(std::fabs(xN(0) - 1.5) < 1e-2 && std::fabs(xN(1) - 1.5) < 1e-2);
   auto& g = fresh.GetKnotPointFunction(0);
@@ -266,6 +283,14 @@ void TestUnicycleAugLag() {
     EXPECT(solver.GetStatus() == SolverStatus::kSolved);
     EXPECT(solver.GetStats().iterations_total == 14);
     EXPECT(solver.GetStats().iterations_outer == 5);
+    {  // example_unicycle_test.cpp:87-88 + the AL log into the open slot (al_solver.hpp:361-362)
+      const altro::SolverStats& st = solver.GetStats();
+      EXPECT(st.cost.size() == 15 && st.violations.size() == 15 && st.max_penalty.size() == 15);
+      EXPECT(st.cost_decrease.back() < solver.GetOptions().cost_tolerance);
+      EXPECT(st.gradient.back() < solver.GetOptions().gradient_tolerance);
+      EXPECT(st.violations.back() < 1e-6 && st.violations.back() >= 0.0);
+      EXPECT(st.max_penalty.back() == solver.GetMaxPenalty() && st.max_penalty.back() > st.max_penalty.front());
+    }
     EXPECT(solver.MaxViolation() < 1e-6);
     const double J = solver.GetiLQRSolver().Cost();
     EXPECT(std::fabs(J - 0.03893465058924039) / 0.03893465058924039 < 1e-9);

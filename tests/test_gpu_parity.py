@@ -602,6 +602,40 @@ def test_large_state_kernels_agree_on_a_ragged_batch(gpu):
         assert e <= tol[k], (k, e)
 
 
+def test_solver_stats_history_against_the_oracle(gpu, oracle):
+    """SolverStats vectors (altro/common/solver_stats.hpp:54-61) recorded on the device, row by row against the
+    oracle's Log()/NewIteration() restatement: cost, alpha, improvement ratio, gradient, cost decrease,
+    regularisation, stored max violation, max penalty — one row per inner iteration of an AL solve."""
+    if gpu._test_engine != "phased":
+        pytest.skip("once (a recording solver runs on the fused engine whatever the default)")
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    B, H = 12, 5
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, B)
+    s.enable_history(instances=H, rows=400)
+    assert s.engine == "fused"
+    s.set_inputs(X0); s.solve_al()
+    r = s.results()
+    plain = gpu.BatchSolver(spec, B)
+    plain.set_inputs(X0); plain.solve_al()
+    assert np.array_equal(plain.results()["cost"].view(np.int64), r["cost"].view(np.int64))  # recording changes nothing
+    names = dict(cost="cost", alpha="alpha", z="z", gradient="gradient", cost_decrease="cost_decrease",
+                 regularization="regularization", violations="violations", max_penalty="max_penalty")
+    for b in range(H):
+        o = oracle_stepper(oracle, spec, X0[b], True)
+        o.solve_al()
+        h = s.history(b)
+        n = int(r["iters"][b, 2])
+        assert len(h["cost"]) == n
+        for k, ok in names.items():
+            ref = o.stat(ok)
+            assert len(ref) == n + 1      # the oracle also holds the open slot
+            err = np.abs(h[k] - ref[:n]) / np.maximum(1.0, np.abs(ref[:n]))
+            assert err.max() <= 1e-8, (b, k, err.argmax(), h[k][err.argmax()], ref[err.argmax()])
+    with pytest.raises(gpu.SolverError, match="instance not recorded"):
+        s.history(H)
+
+
 def test_warm_start_resolve_keeps_duals_and_penalties(gpu, oracle):
     """MPC-style re-solve (docs/Overview.dox:49-54; solver_options.hpp:47-48): second Solve() from
     the previous solution with reset_duals = false and initial_penalty = 0 keeps duals and

@@ -3,7 +3,11 @@ a batch of controllers re-solves every control tick from the previous solution s
 knot, with reset_duals = false and initial_penalty = 0 (solver_options.hpp:47-48,
 al_solver.hpp:292-297), everything device-resident.  Reports latency per tick.
 
-    python tools/mpc_latency.py [batch] [ticks]        (run under gpurun)
+    python tools/mpc_latency.py [batch] [ticks] [cap]  (run under gpurun)
+
+cap > 0 bounds the work of a tick the way a real-time controller does, with the reference's own options
+(max_iterations_total = max_iterations_inner = cap, solver_options.hpp:20-22): the tick then returns the best
+iterate found in `cap` iLQR iterations instead of iterating every controller to convergence.
 """
 import json
 import os
@@ -22,6 +26,7 @@ from altro_cpp_b200 import problems as P  # noqa: E402
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
     ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    cap = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
     n, m, N = spec.n, spec.m, spec.N
     dev = torch.device("cuda", 0)
@@ -44,6 +49,9 @@ def main():
         o = pkg.default_options()
         o.reset_duals = 0
         o.initial_penalty = 0.0
+        if cap > 0:
+            o.max_iterations_total = cap
+            o.max_iterations_inner = cap
         s.set_options(o)
         for t in range(ticks):
             s.trajectory_dev(Xd.data_ptr(), Ud.data_ptr(), stream=stream)
@@ -58,13 +66,15 @@ def main():
     r = s.results()
     print(json.dumps({
         "workload": "C2 unicycle 3 obstacles, warm-started re-solve per tick (reset_duals=0, initial_penalty=0)",
-        "batch": B, "engine": s.engine, "ticks": ticks, "cold_solve_ms": cold,
+        "batch": B, "engine": s.engine, "ticks": ticks, "iteration_cap_per_tick": cap or None, "cold_solve_ms": cold,
         "cold_mean_iterations": float(cold_res["iters"][:, 2].mean()),
         "tick_ms_median": float(np.median(lat)), "tick_ms_p90": float(np.percentile(lat, 90)),
         "tick_ms_first": lat[0], "ticks_per_s_per_controller_batch": 1e3 / float(np.median(lat)),
         "controller_solves_per_s": B * 1e3 / float(np.median(lat)),
         "last_tick_mean_iterations": float(r["iters"][:, 2].mean()),
-        "last_tick_solved_fraction": float((r["status"] == 0).mean())}))
+        "last_tick_max_iterations": int(r["iters"][:, 2].max()),
+        "last_tick_solved_fraction": float((r["status"] == 0).mean()),
+        "last_tick_max_violation_median": float(np.median(r["viol"]))}))
 
 
 if __name__ == "__main__":

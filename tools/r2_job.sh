@@ -11,7 +11,7 @@ if has c3; then timeout 200 python bench.py --workload c3 --steps 3 --warmup 3 -
 if has c4; then timeout 300 python bench.py --workload c4 --steps 2 --warmup 3 --cpu-sample 128 > $OUT/bench_c4.json 2> $OUT/bench_c4.err; fi
 if has c5; then timeout 200 python bench.py --workload c5 --steps 3 --warmup 3 --cpu-sample 256 > $OUT/bench_c5.json 2> $OUT/bench_c5.err; fi
 if has stats; then timeout 400 python tools/gpu_parity_stats.py c2:16384:2048 c3:8192:1024 c4:2048:128 > $OUT/parity_stats.log 2>&1; fi
-if has mpc; then timeout 200 python tools/mpc_latency.py 1024 16 > $OUT/mpc_1024.json 2>&1; fi
+if has mpc; then timeout 200 python tools/mpc_latency.py 1024 16 > $OUT/mpc_1024.json 2>&1; timeout 200 python tools/mpc_latency.py 1024 16 10 > $OUT/mpc_1024_cap10.json 2>&1; timeout 200 python tools/mpc_latency.py 1 16 > $OUT/mpc_1.json 2>&1; fi
 if has launches; then
   timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches.csv python tools/gpu_one_solve.py phased 16384 > $OUT/one.log 2>&1
   python tools/launch_summary.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1
