@@ -631,7 +631,9 @@ def test_solver_stats_history_against_the_oracle(gpu, oracle):
             ref = o.stat(ok)
             assert len(ref) == n + 1      # the oracle also holds the open slot
             err = np.abs(h[k] - ref[:n]) / np.maximum(1.0, np.abs(ref[:n]))
-            assert err.max() <= 1e-8, (b, k, err.argmax(), h[k][err.argmax()], ref[err.argmax()])
+            # z = (J0 - J) / expected is a quotient of two differences: 1e-12 in J shows as 1e-6 in z late in a solve
+            tol = 1e-5 if k == "z" else 1e-8
+            assert err.max() <= tol, (b, k, err.argmax(), h[k][err.argmax()], ref[err.argmax()])
     with pytest.raises(gpu.SolverError, match="instance not recorded"):
         s.history(H)
 
