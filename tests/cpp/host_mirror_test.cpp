@@ -219,7 +219,8 @@ void TestUnicycleILQR() {
   EXPECT(solver.GetStats().alpha.size() == 1 && solver.GetStats().alpha[0] == 0.0625);
   solver.UpdateConvergenceStatistics();
   EXPECT(solver.GetStats().iterations_inner == 1 && solver.GetStats().cost_decrease.size() == 2);
-  EXPECT(solver.GetStats().cost_decrease[0] > 0.0 && solver.GetStats().gradient[0] > 0.0);
+  // without Solve() nobody set stats.initial_cost: dJ = 0 - J (ilqr.hpp:573-574), exactly like the reference
+  EXPECT(solver.GetStats().cost_decrease[0] < 0.0 && solver.GetStats().gradient[0] > 0.0);
 
   // unicycle_ilqr_test.cpp:40-54: cost-to-go gradient and feedforward gain at knot 0
   auto step = def.MakeSolver();
