@@ -186,7 +186,11 @@ __global__ void __launch_bounds__(kWarp) k_backward_coop(SolverParams P) {
           S.Quu[r + col * m] = e[(oLuu + r + col * m) * W] + acc;
         }
       }
-      __syncwarp();  // every lane of the warp is done with the ring slot (and each pair with phase 2)
+      // every lane of the warp is done with the ring slot (its values went straight into the products above, so
+      // the loads have completed); the proxy fence orders those generic-proxy reads before the async-proxy
+      // refill (see k_backward_mat)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
       if (next_k >= 0) {
         if (lane == 0) load_slot(issued % kStages, next_k);
         --next_k;

@@ -1266,6 +1266,9 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 // line-search kernels (phased.cuh).  The kernel touches nothing but the records, K, d and a few scalars per
 // instance: the gain statistic of a failed search (sum_k max_i |d_i|/(|u_i|+1), which needs the
 // controls) is formed by the line-search kernel that observes the failure.
+#ifndef ALTRO_BP_REFILL_EARLY
+#define ALTRO_BP_REFILL_EARLY 0
+#endif
 template <class M, int W, int kStages, bool kStoreCtg, bool kPhased = false>
 __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
   constexpr int n = M::n, m = M::m, nexp = Lane<M, W>::nexp, TPW = kWarp / W;
@@ -1350,12 +1353,16 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
       for (int q = 0; q < n; ++q) lx[q] = e[(f++) * W];
       ALTRO_UNROLL
       for (int q = 0; q < m; ++q) lu[q] = e[(f++) * W];
-      __syncwarp();  // every lane has read the slot -> it can be refilled
+#if ALTRO_BP_REFILL_EARLY
+      // (experiment) refill right after the reads, ordered by a generic -> async proxy fence only
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
       if (next_k >= 0) {
         if (lane == 0) load_slot(issued % kStages, next_k);
         --next_k;
         ++issued;
       }
+#endif
       if (live) {
         double K[m * n], d[m];
         const bool ok =
@@ -1384,6 +1391,21 @@ __global__ void __launch_bounds__(kWarp) k_backward_mat(SolverParams P) {
           if (k == 0) repeat = false;
         }
       }
+#if !ALTRO_BP_REFILL_EARLY
+      // Refill the slot only now.  The TMA write is an async-proxy access: nothing orders it after the
+      // generic-proxy loads above except their COMPLETION, and a load is only known to be complete once its
+      // value has been used — the Riccati step has consumed all 47 of them.  Issuing the refill right
+      // after the loads (round 1) let a bulk copy that hit L2 overtake loads still queued behind a busy
+      // LSU: with other kernels resident on the SM, one tile of a warp occasionally read the last rows
+      // of its record (lx, lu — the last loads issued) from the NEXT occupant of the slot.
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (next_k >= 0) {
+        if (lane == 0) load_slot(issued % kStages, next_k);
+        --next_k;
+        ++issued;
+      }
+#endif
     }
   }
   if (valid) {

@@ -114,3 +114,44 @@ def test_sharded_solver_is_bit_identical_to_single(gpu):
         assert np.array_equal(_bits(a[k]), _bits(b[k])), k
     t = sharded.timings()
     assert t["solve_ms"].shape == (3,) and np.all(t["solve_ms"] > 0)
+
+
+def test_results_do_not_depend_on_other_kernels_running(gpu):
+    """Round-1/2 defect: the TMA ring of the backward-pass kernel refilled a slot right after reading it, with
+    nothing ordering the async-proxy write after the generic-proxy loads; when unrelated kernels kept the SM's
+    load/store pipeline busy, a refill that hit L2 overtook the last loads of a slot and one tile read rows of the
+    wrong knot (18 of 20 solves differed under this load; tools/gpu_flaky*.py).  Repeated solves while copies and
+    GEMMs run on another stream must be bit-identical to a solve on the idle GPU."""
+    import threading
+    import torch
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    B = 1000
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, B)
+    ref = s.solve_al_host(X0)
+    dev = torch.device("cuda", 0)
+    stop = []
+
+    def load():
+        s2 = torch.cuda.Stream(device=dev)
+        a = torch.empty(1 << 26, dtype=torch.float64, device=dev)
+        b = torch.empty_like(a)
+        m1 = torch.randn(4096, 4096, device=dev, dtype=torch.float32)
+        with torch.cuda.stream(s2):
+            while not stop:
+                for _ in range(4):
+                    b.copy_(a)
+                    m1 = (m1 @ m1).clamp_(-1, 1)
+                s2.synchronize()
+
+    t = threading.Thread(target=load, daemon=True)
+    t.start()
+    try:
+        for rep in range(12):
+            out = s.solve_al_host(X0)
+            bad = {k: int((_bits(out[k]) != _bits(ref[k])).reshape(B, -1).any(axis=1).sum())
+                   for k in ("status", "iters", "cost", "viol", "X", "U")}
+            assert not any(bad.values()), f"solve {rep} under load: instances differing per field {bad}"
+    finally:
+        stop.append(1)
+        t.join(timeout=20)

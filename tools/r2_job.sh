@@ -33,6 +33,17 @@ if has bpalone; then
   python tools/ncu_summarize.py $OUT/bp_insolve.ncu-rep $OUT/ncu_k_backward_mat_insolve_fullbatch_summary.txt > /dev/null 2>&1
   rm -f $OUT/bp_insolve.ncu-rep
 fi
+if has c5cap; then
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_solve_large_mma -s 1 -c 1 -o $OUT/c5_mma -f python tools/gpu_c5_one.py 4096 > $OUT/c5_mma.log 2>&1
+  python tools/ncu_summarize.py $OUT/c5_mma.ncu-rep $OUT/ncu_k_solve_large_mma_summary.txt > /dev/null 2>&1
+  rm -f $OUT/c5_mma.ncu-rep
+fi
+if has c3cap; then
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_backward_coop -s 1 -c 1 -o $OUT/c3_coop -f python tools/gpu_one_solve.py phased 8192 0 c3 > $OUT/c3_coop.log 2>&1
+  python tools/ncu_summarize.py $OUT/c3_coop.ncu-rep $OUT/ncu_k_backward_coop_c3_summary.txt > /dev/null 2>&1
+  rm -f $OUT/c3_coop.ncu-rep
+  timeout 200 python bench.py --workload c3 --batch 65536 --steps 3 --warmup 3 --no-cpu --no-extras > $OUT/bench_c3_b65536.json 2> $OUT/bench_c3_b65536.err
+fi
 ls -la $OUT
 cat $OUT/tests.log 2>/dev/null | tail -8
 head -c 1500 $OUT/bench_c2.json 2>/dev/null
