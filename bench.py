@@ -116,7 +116,11 @@ def profiled_traffic():
     import glob
     import re
     best = None
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_backward_mat_phased_summary.txt"))):
+    # preferred: the capture of the very launch `roofline` times (altro_b200_backward_pass_insolve, full batch);
+    # else the same kernel captured inside a solve (its 25th launch: still the full batch)
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_backward_mat_phased_summary.txt"))) + \
+        sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_k_backward_mat_insolve_fullbatch_summary.txt")))
+    for path in paths:
         txt = open(path).read()
         rd = re.search(r"dram__bytes_read\.sum \[Mbyte\] = ([0-9.]+)", txt)
         wr = re.search(r"dram__bytes_write\.sum \[Mbyte\] = ([0-9.]+)", txt)
