@@ -116,7 +116,8 @@ def test_sharded_solver_is_bit_identical_to_single(gpu):
     assert t["solve_ms"].shape == (3,) and np.all(t["solve_ms"] > 0)
 
 
-def test_results_do_not_depend_on_other_kernels_running(gpu):
+@pytest.mark.parametrize("case", ["c2", "c3", "c4"])
+def test_results_do_not_depend_on_other_kernels_running(gpu, case):
     """Round-1/2 defect: the TMA ring of the backward-pass kernel refilled a slot right after reading it, with
     nothing ordering the async-proxy write after the generic-proxy loads; when unrelated kernels kept the SM's
     load/store pipeline busy, a refill that hit L2 overtook the last loads of a slot and one tile read rows of the
@@ -124,9 +125,13 @@ def test_results_do_not_depend_on_other_kernels_running(gpu):
     GEMMs run on another stream must be bit-identical to a solve on the idle GPU."""
     import threading
     import torch
-    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
-    B = 1000
-    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    if case == "c2":    # k_backward_mat<Unicycle>
+        spec, scale, B, reps = P.unicycle_problem(P.K_THREE_OBSTACLES), P.UNICYCLE_X0_SCALE, 1000, 12
+    elif case == "c3":  # k_backward_coop (two lanes per instance, same ring)
+        spec, scale, B, reps = P.triple_integrator_problem(dof=2, N=50, add_constraints=True), P.TRIPLE_INTEGRATOR_X0_SCALE, 4096, 40
+    else:               # k_backward_mat of a run-time compiled model
+        spec, scale, B, reps = P.cartpole_problem(N=200), P.CARTPOLE_X0_SCALE, 512, 6
+    X0 = P.perturbed_initial_states(spec, B, scale)
     s = gpu.BatchSolver(spec, B)
     ref = s.solve_al_host(X0)
     dev = torch.device("cuda", 0)
@@ -147,7 +152,7 @@ def test_results_do_not_depend_on_other_kernels_running(gpu):
     t = threading.Thread(target=load, daemon=True)
     t.start()
     try:
-        for rep in range(12):
+        for rep in range(reps):
             out = s.solve_al_host(X0)
             bad = {k: int((_bits(out[k]) != _bits(ref[k])).reshape(B, -1).any(axis=1).sum())
                    for k in ("status", "iters", "cost", "viol", "X", "U")}
