@@ -26,6 +26,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-split-compile", "0",  # the kernels are independent: let nvcc optimise / assemble them in parallel
+    "-Xfatbin", "-compress-all",  # the cubins (with their -lineinfo tables) compress ~3x; decompressed at load time
     "-Xcompiler", "-fPIC", "-shared",
     "-cudart", "shared",
 ]
@@ -62,7 +63,7 @@ def build(force: bool = False, verbose: bool = False, out: str = LIB, defines=()
             sys.stderr.write(log)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [nvcc, "-shared", "-cudart", "shared", "-o", out] + objs
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", "-o", out] + objs
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -396,8 +396,12 @@ def register_model(name: str, cuda_source: str, n: int, m: int, nparams: int = 0
     return mid.value
 
 
-def precompile_model(model_id: int) -> str:
-    """Compiles the model's kernels into the on-disk module cache now (NVRTC; needs no GPU) -> cache file."""
+def precompile_model(model_id: int, n: int = 0, m: int = 0) -> str:
+    """Compiles the model's kernels into the on-disk module cache now (NVRTC; needs no GPU) -> cache file.
+    n, m: for a built-in model id whose instantiation is produced at run time (triple integrator, dof != 2)."""
     buf = ctypes.create_string_buffer(1024)
-    _check(lib().altro_b200_precompile_model(int(model_id), buf, 1024), "precompile_model")
+    if n or m:
+        _check(lib().altro_b200_precompile_builtin_model(int(model_id), int(n), int(m), buf, 1024), "precompile_model")
+    else:
+        _check(lib().altro_b200_precompile_model(int(model_id), buf, 1024), "precompile_model")
     return buf.value.decode()

@@ -485,12 +485,32 @@ int builtin_cartpole_id() {
   });
   return id;
 }
-int resolve_model(int model) { return model == kCartpole ? builtin_cartpole_id() : model; }
+// Triple integrators other than the perf benchmark's dof = 2 (compiled in) are instantiated at run time from
+// the TripleIntegrator<dof> template of device.cuh: the "plug-in" is one line.  dof <= 3 (n <= 9).
+int builtin_triple_id(int dof) {
+  static std::map<int, int> ids;
+  std::lock_guard<std::mutex> lock(g_plugin_mutex);
+  auto it = ids.find(dof);
+  if (it != ids.end()) return it->second;
+  PluginModel pm;
+  pm.name = "TripleIntegratorDof" + std::to_string(dof);
+  pm.source = "struct " + pm.name + " : TripleIntegrator<" + std::to_string(dof) + "> {};\n";
+  pm.n = 3 * dof; pm.m = dof; pm.nparams = 0;
+  g_plugins.push_back(pm);
+  const int id = kFirstPluginId + static_cast<int>(g_plugins.size()) - 1;
+  ids[dof] = id;
+  return id;
+}
+int resolve_model(int model, int n = 0, int m = 0) {
+  if (model == kCartpole) return builtin_cartpole_id();
+  if (model == kTripleIntegrator && (m == 1 || m == 3) && n == 3 * m) return builtin_triple_id(m);
+  return model;
+}
 
 // out == nullptr: is there a device path for (n, m, model) at tile width W?  (no compilation, no device)
 // Otherwise fills *out; for a plug-in model that may compile or load its module on the CURRENT device.
 int lookup_ops_rc(int n, int m, int model, int W, Ops* out) {
-  model = resolve_model(model);
+  model = resolve_model(model, n, m);
   if (model >= kFirstPluginId) {
     {
       std::lock_guard<std::mutex> lock(g_plugin_mutex);
@@ -511,7 +531,6 @@ int lookup_ops_rc(int n, int m, int model, int W, Ops* out) {
   if (model == kUnicycle && n == 3 && m == 2) ok = ops_for_width<Unicycle>(W, out);
 #ifndef ALTRO_DEV_BUILD
   else if (model == kTripleIntegrator && n == 6 && m == 2) ok = ops_for_width<TripleIntegrator<2>>(W, out);
-  else if (model == kTripleIntegrator && n == 3 && m == 1) ok = ops_for_width<TripleIntegrator<1>>(W, out);
   else if (model == kLinear && n == 32 && m == 8) { if (out) *out = make_large_ops_32_8(); ok = true; }
 #endif
   return ok ? 0 : ALTRO_B200_ERR_UNSUPPORTED;
@@ -826,8 +845,14 @@ int altro_b200_register_model(const char* name, const char* cuda_source, int n, 
   *model_id = kFirstPluginId + static_cast<int>(g_plugins.size()) - 1;
   return 0;
 }
+static int precompile_impl(int model, char* cache_path, int cache_path_cap);
 int altro_b200_precompile_model(int model, char* cache_path, int cache_path_cap) {
-  model = resolve_model(model);
+  return precompile_impl(resolve_model(model), cache_path, cache_path_cap);
+}
+int altro_b200_precompile_builtin_model(int model, int n, int m, char* cache_path, int cache_path_cap) {
+  return precompile_impl(resolve_model(model, n, m), cache_path, cache_path_cap);
+}
+static int precompile_impl(int model, char* cache_path, int cache_path_cap) {
   PluginModel pm;
   {
     std::lock_guard<std::mutex> lock(g_plugin_mutex);

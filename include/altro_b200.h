@@ -137,6 +137,9 @@ int altro_b200_register_model(const char* name, const char* cuda_source, int n, 
 /* compile the model's module into the on-disk cache now (NVRTC only: needs no GPU); cache_path
  * (optional) receives the file name */
 int altro_b200_precompile_model(int model_id, char* cache_path, int cache_path_cap);
+/* the same for a built-in model id whose (n, m) instantiation is produced at run time
+ * (ALTRO_B200_MODEL_TRIPLE_INTEGRATOR with dof = m other than 2; ALTRO_B200_MODEL_CARTPOLE) */
+int altro_b200_precompile_builtin_model(int model, int n, int m, char* cache_path, int cache_path_cap);
 
 /* SetConstraint(GoalConstraint(xf), k)  — Equality; examples/basic_constraints.hpp:15-40 */
 int altro_b200_problem_add_goal(altro_b200_problem* p, int k, const double* xf);

@@ -101,3 +101,25 @@ def test_cartpole_runs_as_a_plugin(oracle):
     assert np.abs(out["X"] - ref["X"]).max() <= 1e-6
     so = os.path.join(ROOT, "altro_cpp_b200", "libaltro_b200.so")
     assert open(so, "rb").read().find(b"NS_8CartpoleE") < 0  # no kernel instantiated on it inside the library
+
+
+@pytest.mark.gpu
+def test_triple_integrator_with_one_degree_of_freedom_is_instantiated_at_run_time():
+    """ALTRO_B200_MODEL_TRIPLE_INTEGRATOR with dof = 1 (n = 3, m = 1) is not compiled into the library: the
+    TripleIntegrator<dof> template of device.cuh is instantiated by NVRTC (module pre-compiled by build()).
+    Constrained AL solve against the oracle."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (the product path has no CPU fallback)")
+    import altro_cpp_b200 as pkg
+    from altro_cpp_b200 import problems as P
+    from oracle import binding as ob
+    pkg.set_default_engine(None)
+    spec = P.triple_integrator_problem(dof=1, N=30, add_constraints=True)
+    B = 40
+    X0 = P.perturbed_initial_states(spec, B, P.TRIPLE_INTEGRATOR_X0_SCALE)
+    out = pkg.BatchSolver(spec, B).solve_al_host(X0)
+    ref = ob.solve_batch(spec, X0, nthreads=4, want_gains=False)
+    assert np.array_equal(out["status"], ref["status"]) and np.array_equal(out["iters"], ref["iters"])
+    assert np.abs(out["X"] - ref["X"]).max() <= 1e-8 * max(1.0, np.abs(ref["X"]).max())
+    assert np.abs(out["cost"] - ref["cost"]).max() <= 1e-9 * max(1.0, np.abs(ref["cost"]).max())
