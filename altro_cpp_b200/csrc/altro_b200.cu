@@ -1350,18 +1350,28 @@ static int solve_phased_impl(altro_b200_solver* s, int mode, cudaStream_t st) {
   // the fused line-search kernels, which loop
   // ... and only pays when few instances are in flight (the slot is then bound by the length of
   // the serial chains, not by instruction throughput)
+  const int kEarlySlots = env_int("ALTRO_B200_EARLY_SLOTS", 8);
   const int split_max = std::min(env_split_max(), s->P.split_cap);
   const bool split_ok = s->P.opt.line_search_max_iterations <= kWarp / kPhasedTile + kWarp;
   for (long slot = 0; slot < 10000000; ++slot) {
     cur->opt = s->P.opt;
     CU(cudaMemsetAsync(cur->counters, 0, 8 * sizeof(int), st));
-    const bool polling = (slot % poll) == 0;
+    // The host learns how many instances are still unreported from a counter the outer step leaves behind.
+    // Early in a solve it asks after every outer step and waits for the answer before queueing the inner
+    // kernels (short solves — two or three iterations — end there, and a no-op slot is ~10 launches); later
+    // every `poll` slots, with the answer read at the end of the slot so the queue never drains.
+    const bool early = slot < kEarlySlots && slot > 0;
+    const bool polling = (slot % poll) == 0 || (early && slot % outer_period == 0);
     if (slot % outer_period == 0) {
       int nl = 0;
       cudaError_t e = cur_ops.outer_step(*cur, mode, s->sm_count, st, &nl);
       s->launches += nl;
       if (e != cudaSuccess) return fail(ALTRO_B200_ERR_CUDA, std::string("outer-step launch: ") + cudaGetErrorString(e));
       if (polling) CU(cudaMemcpyAsync(s->h_count, cur->counters, sizeof(int), cudaMemcpyDeviceToHost, st));
+      if (early) {
+        CU(cudaStreamSynchronize(st));
+        if (s->h_count[0] == 0) break;
+      }
     }
     PH(cur_ops.expansions_phased(*cur, st), "k_update_expansions");
     PH(cur_ops.backward_phased(*cur, st), "k_backward_mat");
