@@ -17,39 +17,44 @@ namespace altro {
 constexpr int kPickHardwareThreads = -1;
 
 struct SolverOptions {
-  int max_iterations_total = 300;
-  int max_iterations_outer = 30;
-  int max_iterations_inner = 100;
-  double cost_tolerance = 1e-4;
-  double gradient_tolerance = 1e-2;
+  // ---- termination (device: altro_b200_options, same names)
+  int max_iterations_total = 300;     // iLQR iterations over a whole AL solve -> kMaxIterations
+  int max_iterations_outer = 30;      // AL (dual-update) iterations -> kMaxOuterIterations
+  int max_iterations_inner = 100;     // iLQR iterations of one AL iteration -> kMaxInnerIterations
+  double cost_tolerance = 1e-4;       // an iLQR solve ends when the cost decrease AND ...
+  double gradient_tolerance = 1e-2;   // ... the normalised feed-forward gain are below these
+  double constraint_tolerance = 1e-4; // the AL solve ends when the max violation is below this
 
-  double bp_reg_increase_factor = 1.6;
+  // ---- backward pass: regularisation of Quu when its LLT fails (ilqr.hpp:401-442 there)
   bool bp_reg_enable = true;
   double bp_reg_initial = 0.0;
-  double bp_reg_max = 1e8;
+  double bp_reg_increase_factor = 1.6;
   double bp_reg_min = 1e-8;
-  int bp_reg_fail_threshold = 100;
-  bool check_forwardpass_bounds = true;
+  double bp_reg_max = 1e8;
+  int bp_reg_fail_threshold = 100;    // restarts at bp_reg_max before kBackwardPassRegularizationFailed
+
+  // ---- forward pass: backtracking line search on alpha = 1, 1/f, 1/f^2, ...
+  int line_search_max_iterations = 20;
+  double line_search_decrease_factor = 2;
+  double line_search_lower_bound = 1e-8;  // accepted when lower <= actual / expected decrease <= upper
+  double line_search_upper_bound = 10.0;
+  bool check_forwardpass_bounds = true;   // a rollout leaving |x| <= state_max, |u| <= control_max is rejected
   double state_max = 1e8;
   double control_max = 1e8;
 
-  int line_search_max_iterations = 20;
-  double line_search_lower_bound = 1e-8;
-  double line_search_upper_bound = 10.0;
-  double line_search_decrease_factor = 2;
+  // ---- augmented Lagrangian
+  double initial_penalty = 1.0;  // every Solve() resets all penalties to this value; 0 keeps them
+  double maximum_penalty = 1e8;  // -> kMaxPenalty
+  bool reset_duals = true;       // false = warm start from the previous solve's multipliers
 
-  double constraint_tolerance = 1e-4;
-  double maximum_penalty = 1e8;
-  double initial_penalty = 1.0;  // every Solve() resets all penalties to this value; 0 disables
-  bool reset_duals = true;
-
-  int header_frequency = 10;
+  // ---- host-side knobs kept for source compatibility; no effect on the device solve
   LogLevel verbose = LogLevel::kSilent;
+  int header_frequency = 10;
   bool profiler_enable = false;
   bool profiler_output_to_file = false;
   std::string log_directory;
   std::string profile_filename = "profiler.out";
-  int nthreads = 1;
+  int nthreads = 1;          // the reference's thread pool; here the batch axis takes its place
   int tasks_per_thread = 1;
 
   int NumThreads() const {

@@ -1,34 +1,36 @@
-// altro/utils/assert.hpp (B200 host mirror) — ALTRO_ASSERT with the reference's contract
-// (altro/utils/assert.hpp:6-10 there): message + abort() in debug builds, compiled out under NDEBUG.
+// altro/utils/assert.hpp (B200 host mirror) — ALTRO_ASSERT(condition, message): the reference's contract
+// (altro/utils/assert.hpp:6-10 there) is "report and abort() in debug builds, nothing under NDEBUG".
+// Contract violations that reach the device library are reported a second time, in every build type, as
+// altro::DeviceError carrying altro_b200_last_error() (altro/device_solver.hpp).
 #pragma once
 
 #include <cstdio>
 #include <cstdlib>
 #include <string>
 
-#ifndef NDEBUG
-#define ALTRO_ASSERT(Expr, Msg) altro::utils::AssertMsg((Expr), Msg, #Expr, __LINE__, __FILE__)
-#else
-#define ALTRO_ASSERT(Expr, Msg) ;
-#endif
-
 namespace altro {
 namespace utils {
 
-inline void AssertMsg(bool expr, const std::string& msg, const char* expr_str, int line, const char* file) {
-  if (!expr) {
-    std::fprintf(stderr, "Assert failed:\t%s\nExpected:\t%s\nSource:\t\t%s, line %d\n", msg.c_str(), expr_str, file, line);
-    std::abort();
-  }
-}
-
-constexpr bool AssertionsActive() {
-#ifndef NDEBUG
-  return true;
+#if defined(NDEBUG)
+constexpr bool kAssertionsCompiledIn = false;
 #else
-  return false;
+constexpr bool kAssertionsCompiledIn = true;
 #endif
+constexpr bool AssertionsActive() { return kAssertionsCompiledIn; }
+
+// prints what was expected, where, and the caller's message; then aborts
+inline void AssertMsg(bool holds, const std::string& message, const char* condition_text, int line, const char* file) {
+  if (holds) return;
+  std::fprintf(stderr, "%s:%d: ALTRO_ASSERT(%s) failed: %s\n", file, line, condition_text, message.c_str());
+  std::abort();
 }
 
 }  // namespace utils
 }  // namespace altro
+
+#if defined(NDEBUG)
+#define ALTRO_ASSERT(condition, message) ;
+#else
+#define ALTRO_ASSERT(condition, message) \
+  ::altro::utils::AssertMsg(static_cast<bool>(condition), (message), #condition, __LINE__, __FILE__)
+#endif
