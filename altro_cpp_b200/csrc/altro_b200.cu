@@ -1516,6 +1516,7 @@ int altro_b200_update_convergence_statistics(altro_b200_solver* s, void* stream)
   return phase_impl(s, kPhaseStats, S(stream));
 }
 int altro_b200_update_duals(altro_b200_solver* s, void* stream) { return phase_impl(s, kPhaseDuals, S(stream)); }
+int altro_b200_al_init(altro_b200_solver* s, void* stream) { return phase_impl(s, kPhaseAlInit, S(stream)); }
 int altro_b200_update_penalties(altro_b200_solver* s, void* stream) {
   return phase_impl(s, kPhasePenalties, S(stream));
 }

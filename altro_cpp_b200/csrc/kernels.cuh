@@ -988,6 +988,7 @@ enum Phase : int {
   kPhaseDuals,
   kPhasePenalties,
   kPhaseSolveSetup,
+  kPhaseAlInit,
 };
 
 template <class M, int W>
@@ -1120,6 +1121,23 @@ __global__ void __launch_bounds__(kSolveWarps* kWarp) k_phase(SolverParams P, in
     }
     case kPhasePenalties: {  // UpdatePenalties(), al_solver.hpp:347-355
       if (lead) L.sc(S_PENALTY) = penalty * o.penalty_scaling;
+      break;
+    }
+    case kPhaseAlInit: {  // AugmentedLagrangianiLQR::Init(), al_solver.hpp:287-302 (what a whole solve does first)
+      if (lead) {
+        if (o.reset_duals && P.pmax > 0) {
+          for (int k = 0; k <= N; ++k) {
+            double* lam = L.lam(k);
+            for (int r = 0; r < P.pmax; ++r) lam[r * W] = 0.0;
+          }
+        }
+        if (o.initial_penalty > 0) L.sc(S_PENALTY) = o.initial_penalty;
+        L.is(I_ITERS_OUTER) = 0;  // stats.Reset()
+        L.is(I_ITERS_TOTAL) = 0;
+        L.sc(S_COST_CUR) = 0.0;
+        L.sc(S_COST_PREV) = 0.0;
+        L.is(I_STATUS_AL) = kUnsolved;
+      }
       break;
     }
   }

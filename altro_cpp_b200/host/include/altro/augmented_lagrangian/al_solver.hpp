@@ -57,12 +57,22 @@ class AugmentedLagrangianiLQR {
 
   void Solve() {
     auto Z = ilqr_solver_.GetTrajectory();
+    ALTRO_ASSERT(Z != nullptr, "Invalid trajectory pointer. May be uninitialized.");
     if (!Z) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
     core_->Upload(*Z);
     core_->Run(detail::DeviceSolver::kSolveAL);
     core_->Download(Z.get());
     core_->Pull();
     core_->PullHistory();
+  }
+  // what Solve() does first (al_solver.hpp:287-302 there): duals reset if reset_duals, penalties set to
+  // initial_penalty if that is positive, statistics cleared.  Needs the trajectory (it sizes the device solver).
+  void Init() {
+    auto Z = ilqr_solver_.GetTrajectory();
+    if (!Z) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
+    core_->Upload(*Z);
+    core_->Run(detail::DeviceSolver::kAlInit);
+    GetStats().Reset();
   }
   void UpdateDuals() { core_->Run(detail::DeviceSolver::kUpdateDuals); }
   void UpdatePenalties() { core_->Run(detail::DeviceSolver::kUpdatePenalties); }

@@ -8,6 +8,7 @@
 // parameters (altro/device_registry.hpp); everything numerical then happens on the device.
 #pragma once
 
+#include <cstdio>
 #include <type_traits>
 
 #include "altro/eigentypes.hpp"
@@ -38,30 +39,58 @@ class FunctionBase {
   }
   virtual bool HasHessian() const = 0;
 
-  // finite-difference check of the user's Jacobian at (x, u)
+  // ---- finite-difference checks of the user's derivatives (host-side debugging aids; tolerance on the
+  // Frobenius norm of the difference).  Without arguments: at a random point of the functor's own sizes.
   bool CheckJacobian(const VectorXdRef& x, const VectorXdRef& u, double eps = kDefaultTolerance, bool verbose = false) {
     const int n = static_cast<int>(x.size()), m = static_cast<int>(u.size()), p = OutputDimension();
-    VectorXd z(n + m);
-    for (int i = 0; i < n; ++i) z(i) = x(i);
-    for (int j = 0; j < m; ++j) z(n + j) = u(j);
-    auto f = [&](const VectorXd& zz, VectorXd& out) {
-      VectorXd xx(n), uu(m);
-      for (int i = 0; i < n; ++i) xx(i) = zz(i);
-      for (int j = 0; j < m; ++j) uu(j) = zz(n + j);
-      Evaluate(xx, uu, out);
+    MatrixXd analytic = MatrixXd::Zero(p, n + m);
+    Jacobian(x, u, analytic);
+    auto stacked = [this, n, m, p](const VectorXd& z) -> VectorXd {
+      VectorXd out = VectorXd::Zero(p);
+      this->Evaluate(z.head(n), z.tail(m), out);
+      return out;
     };
-    const MatrixXd fd = utils::FiniteDiffJacobian(f, z, p);
-    MatrixXd jac = MatrixXd::Zero(p, n + m);
-    Jacobian(x, u, jac);
-    const double err = (fd - jac).template lpNorm<Eigen::Infinity>();
-    if (verbose) std::fprintf(stderr, "CheckJacobian: max |fd - jac| = %g\n", err);
-    return err < eps;
+    const MatrixXd numeric = utils::FiniteDiffJacobian<Eigen::Dynamic, Eigen::Dynamic>(stacked, Stack(x, u));
+    return Agree(numeric, analytic, eps, verbose, "Jacobian");
   }
   bool CheckJacobian(double eps = kDefaultTolerance, bool verbose = false) {
     return CheckJacobian(VectorXd::Random(StateDimension()), VectorXd::Random(ControlDimension()), eps, verbose);
   }
+  // Hessian of b' f(x, u) with respect to (x, u)
+  bool CheckHessian(const VectorXdRef& x, const VectorXdRef& u, const VectorXdRef& b, double eps = kDefaultTolerance,
+                    bool verbose = false) {
+    const int n = StateDimension(), m = ControlDimension(), p = OutputDimension();
+    MatrixXd analytic = MatrixXd::Zero(n + m, n + m);
+    Hessian(x, u, b, analytic);
+    const VectorXd weights = b;
+    auto weighted = [this, n, m, p, &weights](const VectorXd& z) -> double {
+      VectorXd out = VectorXd::Zero(p);
+      this->Evaluate(z.head(n), z.tail(m), out);
+      return out.dot(weights);
+    };
+    const MatrixXd numeric = utils::FiniteDiffHessian<Eigen::Dynamic>(weighted, Stack(x, u));
+    return Agree(numeric, analytic, eps, verbose, "Hessian");
+  }
+  bool CheckHessian(double eps = kDefaultTolerance, bool verbose = false) {
+    const int p = OutputDimension();
+    VectorXd b = (p == 1) ? VectorXd::Ones(p) : VectorXd::Random(p);
+    return CheckHessian(VectorXd::Random(StateDimension()), VectorXd::Random(ControlDimension()), b, eps, verbose);
+  }
 
  protected:
+  static VectorXd Stack(const VectorXdRef& x, const VectorXdRef& u) {
+    VectorXd z(x.size() + u.size());
+    for (int i = 0; i < x.size(); ++i) z(i) = x(i);
+    for (int j = 0; j < u.size(); ++j) z(x.size() + j) = u(j);
+    return z;
+  }
+  template <class A, class B>
+  static bool Agree(const A& numeric, const B& analytic, double eps, bool verbose, const char* what) {
+    const double err = (numeric - analytic).norm();
+    if (verbose) std::fprintf(stderr, "Check%s: |finite difference - analytic| = %g (tolerance %g)\n", what, err, eps);
+    return err < eps;
+  }
+
   static constexpr double kDefaultTolerance = 1e-4;
 };
 
@@ -90,6 +119,18 @@ class ScalarFunction : public FunctionBase {
     Hessian(x, u, hess);
   }
   bool HasHessian() const override { return true; }
+
+  bool CheckGradient(const VectorXdRef& x, const VectorXdRef& u, double eps = kDefaultTolerance, bool verbose = false) {
+    const int n = static_cast<int>(x.size()), m = static_cast<int>(u.size());
+    VectorXd analytic = VectorXd::Zero(n + m);
+    Gradient(x, u, analytic);
+    auto stacked = [this, n, m](const VectorXd& z) -> double { return this->Evaluate(z.head(n), z.tail(m)); };
+    const VectorXd numeric = utils::FiniteDiffGradient<Eigen::Dynamic>(stacked, Stack(x, u));
+    return Agree(numeric, analytic, eps, verbose, "Gradient");
+  }
+  bool CheckGradient(double eps = kDefaultTolerance, bool verbose = false) {
+    return CheckGradient(VectorXd::Random(StateDimension()), VectorXd::Random(ControlDimension()), eps, verbose);
+  }
 };
 
 }  // namespace altro

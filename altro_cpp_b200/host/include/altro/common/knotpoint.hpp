@@ -29,7 +29,10 @@ class KnotPoint : public StateControlSized<n, m> {
       : StateControlSized<n, m>(z.StateDimension(), z.ControlDimension()), x_(z.State()), u_(z.Control()),
         t_(z.GetTime()), h_(z.GetStep()) {}
 
-  static KnotPoint Random() { return Random(n, m); }
+  static KnotPoint Random() {
+    ALTRO_ASSERT(n > 0 && m > 0, "Must pass in size if state or control dimension is unknown at compile time.");
+    return Random(n, m);
+  }
   static KnotPoint Random(int state_dim, int control_dim) {
     const StateVector x = StateVector::Random(state_dim);
     const ControlVector u = ControlVector::Random(control_dim);

@@ -64,6 +64,10 @@ class SolverStats {
     for (auto& kv : floats_) kv.second->clear();
     SetCapacity(opts_.max_iterations_total);
     logger_.SetLevel(opts_.verbose);
+    // the profiler follows the options of the moment, like everything else Reset() re-reads
+    if (opts_.profiler_enable) timer_->Activate();
+    else timer_->Deactivate();
+    if (opts_.profiler_output_to_file) ProfilerOutputToFile(true);
   }
   void SetTolerances(const double&, const double&, const double&) {}
   void SetVerbosity(LogLevel level) { logger_.SetLevel(level); }

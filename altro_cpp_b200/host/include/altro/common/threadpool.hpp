@@ -23,6 +23,15 @@ class ThreadPool {
   ThreadPool() = default;
   ThreadPool(const ThreadPool&) = delete;
   ThreadPool& operator=(const ThreadPool&) = delete;
+  // a stopped pool can be moved: its pending tasks (and what Wait() will wait for) move with it
+  ThreadPool(ThreadPool&& other) noexcept { TakeFrom(other); }
+  ThreadPool& operator=(ThreadPool&& other) noexcept {
+    if (this != &other) {
+      if (IsRunning()) StopThreads();
+      TakeFrom(other);
+    }
+    return *this;
+  }
   ~ThreadPool() {
     if (IsRunning()) StopThreads();
   }
@@ -68,6 +77,14 @@ class ThreadPool {
   void SetTimeoutPerTask(std::chrono::duration<Rep, Period>) {}
 
  private:
+  void TakeFrom(ThreadPool& other) {
+    ALTRO_ASSERT(!other.IsRunning(), "Stop the threads of a pool before moving it.");
+    std::lock_guard<std::mutex> lock(other.mutex_);
+    queue_ = std::move(other.queue_);
+    futures_ = std::move(other.futures_);
+    other.queue_.clear();
+    other.futures_.clear();
+  }
   void Work() {
     for (;;) {
       std::packaged_task<void()> task;

@@ -4,6 +4,7 @@
 // observability; device time is measured with CUDA events (bench.py).
 #pragma once
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <map>
@@ -28,17 +29,9 @@ class Timer : public std::enable_shared_from_this<Timer> {
   static std::shared_ptr<Timer> MakeUnique() { return std::shared_ptr<Timer>(new Timer()); }
   inline Stopwatch Start(const std::string& name);
   void PrintSummary() { PrintSummary(&times_); }
-  void PrintSummary(std::map<std::string, microseconds>* times) {
-    microseconds total(0);
-    for (const auto& kv : *times)
-      if (kv.first.find('/') == std::string::npos) total += kv.second;
-    std::fprintf(io_, "%-40s %12s %8s\n", "Description", "Time (us)", "%Total");
-    for (const auto& kv : *times)
-      std::fprintf(io_, "%-40s %12lld %8.1f\n", kv.first.c_str(), static_cast<long long>(kv.second.count()),
-                   total.count() ? 100.0 * static_cast<double>(kv.second.count()) / static_cast<double>(total.count()) : 0.0);
-    std::fflush(io_);
-    printed_summary_ = true;
-  }
+  // One line per name stack, children indented under their parent, with the share of the whole run and of the
+  // parent (altro/common/profile_entry.hpp).  The map's order puts "a/b" right after "a".
+  inline void PrintSummary(std::map<std::string, microseconds>* times);
   void Activate() { active_ = true; }
   void Deactivate() { active_ = false; }
   bool IsActive() const { return active_; }
@@ -91,6 +84,38 @@ class Stopwatch {
   std::chrono::time_point<std::chrono::high_resolution_clock> start_;
   std::shared_ptr<Timer> parent_;
 };
+
+}  // namespace altro
+
+#include "altro/common/profile_entry.hpp"
+
+namespace altro {
+
+inline void Timer::PrintSummary(std::map<std::string, microseconds>* times) {
+  std::vector<ProfileEntry::Ptr> entries, open_levels;  // open_levels[l] = the last entry seen with l name parts
+  entries.emplace_back(std::make_shared<ProfileEntry>("top", microseconds(0)));
+  open_levels.emplace_back(entries.front());
+  int width = 11;  // "Description"
+  for (const auto& kv : *times) {
+    ProfileEntry::Ptr entry = std::make_shared<ProfileEntry>(kv.first, kv.second);
+    const std::size_t level = entry->NumLevels();
+    if (level >= open_levels.size()) open_levels.resize(level + 1);
+    open_levels[level] = entry;
+    entry->parent = open_levels[level - 1] ? open_levels[level - 1] : entries.front();
+    if (level == 1) entries.front()->time += entry->time;
+    width = std::max(width, static_cast<int>(2 * (level - 1) + entry->name.back().size()));
+    entries.emplace_back(std::move(entry));
+  }
+  width += 2;
+  std::fprintf(io_, "%-*s  %9s  %7s  %7s\n", width, "Description", "Time (us)", "%Total", "%Parent");
+  std::fprintf(io_, "%s\n", std::string(static_cast<std::size_t>(width) + 31, '-').c_str());
+  for (std::size_t i = 1; i < entries.size(); ++i) {
+    entries[i]->CalcStats();
+    entries[i]->Print(io_, width);
+  }
+  std::fflush(io_);
+  printed_summary_ = true;
+}
 
 inline Stopwatch Timer::Start(const std::string& name) {
   if (!active_) return Stopwatch();

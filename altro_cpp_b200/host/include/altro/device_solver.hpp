@@ -150,6 +150,7 @@ class DeviceSolver {
     kUpdateConvergenceStatistics,
     kUpdateDuals,
     kUpdatePenalties,
+    kAlInit,
     kSolveSetup,
     kSolveILQR,
     kSolveAL
@@ -182,6 +183,7 @@ class DeviceSolver {
       case kUpdateConvergenceStatistics: rc = altro_b200_update_convergence_statistics(solver_, nullptr); break;
       case kUpdateDuals: rc = altro_b200_update_duals(solver_, nullptr); break;
       case kUpdatePenalties: rc = altro_b200_update_penalties(solver_, nullptr); break;
+      case kAlInit: rc = altro_b200_al_init(solver_, nullptr); break;
       case kSolveSetup: rc = altro_b200_solve_setup(solver_, nullptr); break;
       case kSolveILQR: rc = altro_b200_solve_ilqr(solver_, nullptr); break;
       case kSolveAL: rc = altro_b200_solve_al(solver_, nullptr); break;

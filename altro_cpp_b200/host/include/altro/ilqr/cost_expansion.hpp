@@ -4,8 +4,12 @@
 // GetKnotPointFunction(k) hands out.
 #pragma once
 
+#include <memory>
+
+#include "altro/common/knotpoint.hpp"
 #include "altro/common/state_control_sized.hpp"
 #include "altro/eigentypes.hpp"
+#include "altro/problem/costfunction.hpp"
 
 namespace altro {
 namespace ilqr {
@@ -45,6 +49,16 @@ class CostExpansion : public StateControlSized<n, m> {
   }
   void SetZero() {
     xx_.setZero(); xu_.setZero(); uu_.setZero(); x_.setZero(); u_.setZero();
+  }
+  // Host-side evaluation through the functor's virtuals (what the reference's solver does every iteration; here a
+  // debugging aid — the solve expands on the device, k_update_expansions)
+  void CalcExpansion(const std::shared_ptr<problem::CostFunction>& costfun, const VectorXdRef& x, const VectorXdRef& u) {
+    costfun->Gradient(x, u, x_, u_);
+    costfun->Hessian(x, u, xx_, xu_, uu_);
+  }
+  template <int n2, int m2, class T>
+  void CalcExpansion(const std::shared_ptr<problem::CostFunction>& costfun, const KnotPoint<n2, m2, T>& z) {
+    CalcExpansion(costfun, z.State(), z.Control());
   }
 
  private:

@@ -185,6 +185,8 @@ class iLQR {
     return *core_;
   }
   void Require() const {
+    // a contract violation first of all (abort in debug builds, like the reference), an error in every build
+    ALTRO_ASSERT(Z_ != nullptr, "Invalid trajectory pointer. May be uninitialized.");
     if (!Z_) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
   }
   void MakeKnotPoints() {

@@ -67,6 +67,8 @@ class Problem {
   void SetConstraint(std::shared_ptr<ConstraintObject> con, int k) {
     using ConType = typename ConstraintObject::ConstraintType;
     constraints::ConstraintPtr<ConType> ptr = con;
+    ALTRO_ASSERT(ptr != nullptr, "Must provide a valid constraint pointer.");
+    ALTRO_ASSERT(ptr->OutputDimension() > 0, "Constraint must have a length greater than zero.");
     AddConstraint(std::move(ptr), k);
   }
 
@@ -97,6 +99,10 @@ class Problem {
     bool ok = true;
     if (initial_state_->size() == 0) {
       if (verbose) std::cerr << "Initial state is not set." << std::endl;
+      ok = false;
+    } else if (models_[0] && models_[0]->StateDimension() != initial_state_->size()) {
+      if (verbose) std::cerr << "The initial state has " << initial_state_->size() << " entries, the first model has "
+                             << models_[0]->StateDimension() << " states." << std::endl;
       ok = false;
     }
     for (int k = 0; k <= N_; ++k) {

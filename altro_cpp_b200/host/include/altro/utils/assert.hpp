@@ -21,7 +21,7 @@ constexpr bool AssertionsActive() { return kAssertionsCompiledIn; }
 // prints what was expected, where, and the caller's message; then aborts
 inline void AssertMsg(bool holds, const std::string& message, const char* condition_text, int line, const char* file) {
   if (holds) return;
-  std::fprintf(stderr, "%s:%d: ALTRO_ASSERT(%s) failed: %s\n", file, line, condition_text, message.c_str());
+  std::fprintf(stderr, "%s:%d: Assertion (%s) failed: %s\n", file, line, condition_text, message.c_str());
   std::abort();
 }
 

@@ -222,6 +222,9 @@ int altro_b200_backward_pass(altro_b200_solver* s, void* stream);       /* ilqr.
 int altro_b200_forward_pass(altro_b200_solver* s, void* stream);        /* ilqr.hpp:512-558 */
 int altro_b200_update_convergence_statistics(altro_b200_solver* s, void* stream); /* :568-587 */
 int altro_b200_update_duals(altro_b200_solver* s, void* stream);        /* al_solver.hpp:336-345 */
+/* AugmentedLagrangianiLQR::Init(): duals reset (reset_duals), penalties set to initial_penalty (> 0), outer and total
+ * iteration counters cleared — al_solver.hpp:287-302.  A whole solve does this itself. */
+int altro_b200_al_init(altro_b200_solver* s, void* stream);
 int altro_b200_update_penalties(altro_b200_solver* s, void* stream);    /* al_solver.hpp:347-355 */
 
 /* SolveSetup(), ilqr.hpp:629-645 (resets iterations_inner, status, regularisation, deltaV) */

@@ -1,0 +1,123 @@
+"""Compiles the reference's UNMODIFIED unit-test sources (test/**/*.cpp, read where they lie under
+/root/reference) against this repo's host mirror (altro_cpp_b200/host/include), the Eigen stand-in and a small
+GoogleTest stand-in (tests/cpp/gtest_standin), links them with libaltro_b200.so and the reference's own
+examples/*.cpp, and runs them.  Nothing of the reference is copied; executables go to tests/_ref_build/unit/.
+
+    python tests/ref_unit_tests.py [test paths relative to /root/reference/test ...]     # try-all report
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "_ref_build", "unit")
+LIBDIR = os.path.join(ROOT, "altro_cpp_b200")
+STANDIN = os.path.join(ROOT, "tests", "cpp", "gtest_standin")
+EXAMPLE_SOURCES = ["examples/unicycle.cpp", "examples/triple_integrator.cpp", "examples/quadratic_cost.cpp",
+                   "examples/basic_constraints.cpp", "examples/obstacle_constraints.cpp",
+                   "examples/problems/unicycle.cpp", "examples/problems/triple_integrator.cpp"]
+
+# Unit tests of the reference that exercise only host-side classes the mirror re-implements: run on the CPU.
+# Not listed: common/trajectory_test.cpp (its fixture reads U[N], one past the end of a std::vector — harmless with
+# Eigen's in-place fixed-size storage, not with the heap-backed stand-in); utils/benchmarking_test.cpp,
+# constraints/constraints_test.cpp, ilqr/ilqr_test.cpp, ilqr/knot_point_functions_test.cpp and
+# augmented_lagrangian/auglag_test.cpp (they test classes internal to the reference's CPU solver —
+# ConstraintValues, ALCost construction, KnotPointFunctions arithmetic — that have no host counterpart here: that
+# arithmetic lives on the device and is pinned by tests/test_oracle_golden.py and tests/test_gpu_parity.py).
+HOST_TESTS = ["common/knotpoint_test.cpp", "common/functionbase_test.cpp", "common/solver_options_test.cpp",
+              "common/solver_logging_test.cpp", "common/timer_test.cpp", "common/threadpool_test.cpp",
+              "problem/problem_test.cpp", "problem/dynamics_test.cpp", "problem/costfunction_test.cpp",
+              "problem/quadratic_cost_test.cpp", "problem/unicycle_test.cpp", "problem/triple_integrator_test.cpp",
+              "utils/derivative_checker_test.cpp", "ilqr/cost_expansion_test.cpp", "ilqr/dynamics_expansion_test.cpp"]
+# Tests that build solvers and solve: compiled here, run on the GPU box (the reference's own golden values —
+# iteration counts, costs, alpha, gains — checked by the reference's own assertions, on the device).
+DEVICE_TESTS = ["ilqr/unicycle_ilqr_test.cpp", "ilqr/ilqr_class_test.cpp", "examples/example_unicycle_test.cpp",
+                "examples/example_triple_integrator_test.cpp"]
+
+
+def exe_path(rel):
+    return os.path.join(OUT, rel.replace("/", "_").replace(".cpp", ""))
+
+
+def fmt_include():
+    try:
+        import torch
+        inc = os.path.join(os.path.dirname(torch.__file__), "include")
+        return inc if os.path.exists(os.path.join(inc, "fmt", "format.h")) else None
+    except Exception:
+        return None
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "test")) and fmt_include() is not None
+
+
+def _flags():
+    inc = ["-I", os.path.join(ROOT, "altro_cpp_b200", "host", "include"), "-I", os.path.join(ROOT, "include"),
+           "-I", STANDIN, "-I", REF, "-I", fmt_include(), "-DFMT_HEADER_ONLY", f'-DLOCAL_LOG_DIR="{OUT}"', f'-DLOGDIR="{OUT}"']
+    return ["g++", "-std=c++14", "-O1", "-w"] + inc   # no -DNDEBUG: the tests exercise ALTRO_ASSERT (EXPECT_DEATH)
+
+
+def build_support():
+    """objects shared by every test program: the reference's examples/*.cpp + the stand-in's main()"""
+    os.makedirs(OUT, exist_ok=True)
+    objs, procs = [], []
+    for src in EXAMPLE_SOURCES:
+        obj = os.path.join(OUT, src.replace("/", "_") + ".o")
+        procs.append((src, subprocess.Popen(_flags() + ["-c", os.path.join(REF, src), "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    main_obj = os.path.join(OUT, "gtest_main.o")
+    procs.append(("gtest_main.cc", subprocess.Popen(_flags() + ["-c", os.path.join(STANDIN, "gtest_main.cc"), "-o", main_obj],
+                                                     stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        log, _ = p.communicate()
+        if p.returncode != 0:
+            raise subprocess.CalledProcessError(p.returncode, src, output=log)
+    return objs + [main_obj]
+
+
+def build_test(rel, support):
+    """-> (exe or None, compiler log)"""
+    exe = exe_path(rel)
+    cmd = _flags() + [os.path.join(REF, "test", rel)] + support + \
+        ["-o", exe, "-L", LIBDIR, "-laltro_b200", f"-Wl,-rpath,{LIBDIR}", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return (exe if r.returncode == 0 else None), (r.stdout + r.stderr)
+
+
+def run_test(exe, timeout=120):
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=timeout)
+    return r.returncode, r.stdout, r.stderr
+
+
+def build_all(tests=None, jobs=8):
+    """-> {rel: (exe or None, log)}; compiles in parallel"""
+    from concurrent.futures import ThreadPoolExecutor
+    tests = list(tests or (HOST_TESTS + DEVICE_TESTS))
+    support = build_support()
+    with ThreadPoolExecutor(max_workers=jobs) as pool:
+        results = list(pool.map(lambda rel: build_test(rel, support), tests))
+    return dict(zip(tests, results))
+
+
+if __name__ == "__main__":
+    tests = sys.argv[1:] or (HOST_TESTS + DEVICE_TESTS)
+    built = build_all(tests)
+    for rel in tests:
+        exe, log = built[rel]
+        if exe is None:
+            first = [l for l in log.splitlines() if "error" in l][:4]
+            print(f"COMPILE-FAIL {rel}\n    " + "\n    ".join(first))
+            continue
+        rc, out, err = run_test(exe)
+        summary = [l for l in out.splitlines() if l.startswith("[====")]
+        failed = [l for l in out.splitlines() if "FAILED" in l]
+        print(f"{'PASS' if rc == 0 else 'FAIL'} {rel}  {summary[-1] if summary else ''}")
+        for l in failed[:8]:
+            print("    " + l)
+        if rc != 0:
+            print("    " + "\n    ".join(err.splitlines()[:12]))
