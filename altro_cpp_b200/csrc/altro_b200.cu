@@ -910,6 +910,17 @@ int altro_b200_problem_set_uniform_step(altro_b200_problem* p, float h) {
   p->step_set = true;
   return 0;
 }
+int altro_b200_problem_set_steps(altro_b200_problem* p, const float* t, const float* h) {
+  if (!p || !t || !h) return fail(ALTRO_B200_ERR_ARG, "set_steps: null argument");
+  for (int k = 0; k < p->N; ++k)
+    if (!(h[k] > 0.0f)) return fail(ALTRO_B200_ERR_ARG, "set_steps: every step before the terminal knot must be positive");
+  for (int k = 0; k <= p->N; ++k) {  // Trajectory::SetStep / SetTime per knot, altro/common/trajectory.hpp:119-120
+    p->h[k] = h[k];
+    p->t[k] = t[k];
+  }
+  p->step_set = true;
+  return 0;
+}
 int altro_b200_problem_set_cost(altro_b200_problem* p, int k0, int k1, const double* Q, const double* R,
                                 const double* H, const double* q, const double* r, double c) {
   if (!p || !Q || !R || !H || !q || !r) return fail(ALTRO_B200_ERR_ARG, "set_cost: null argument");

@@ -62,19 +62,28 @@ class DeviceSolver {
   SolverStats& GetStats() { return stats_; }
 
   // ---- inputs ------------------------------------------------------------------------------
-  // The time step lives in the trajectory (knotpoint.hpp:180 there), the device problem needs it
-  // at creation: the device solver is (re)built when a trajectory with a new step arrives.
-  void SetStep(float h) {
-    if (solver_ && h != h_) {
+  // Times and steps live in the trajectory (knotpoint.hpp:180 there), the device problem needs them at
+  // creation: the device solver is (re)built when a trajectory with another time grid arrives.
+  void SetTimeGrid(const std::vector<float>& t, const std::vector<float>& h) {
+    if (have_step_ && t == t_ && h == h_all_) return;
+    if (solver_) {
       altro_b200_solver_destroy(solver_);
       solver_ = nullptr;
     }
-    if (multi_ && h != h_) {
+    if (multi_) {
       altro_b200_multi_destroy(multi_);
       multi_ = nullptr;
     }
-    h_ = h;
+    t_ = t;
+    h_all_ = h;
     have_step_ = true;
+  }
+  void SetStep(float h) {  // uniform grid, t_k = float(k) * h like Trajectory::SetUniformStep
+    std::vector<float> t(static_cast<size_t>(N_) + 1), hs(static_cast<size_t>(N_) + 1, h);
+    for (int k = 0; k < N_; ++k) t[k] = static_cast<float>(k) * h;
+    t[N_] = static_cast<float>(h) * N_;
+    hs[N_] = 0.0F;
+    SetTimeGrid(t, hs);
   }
   void SetPenalty(double rho) {
     penalty_ = rho;
@@ -94,13 +103,14 @@ class DeviceSolver {
   // Z -> staging -> device: the states and controls of `Z` become those of every instance.
   template <class Traj>
   void Upload(const Traj& Z) {
-    // the device problem carries one uniform step (altro_b200_problem_set_uniform_step): a trajectory
-    // with per-knot steps would silently be solved with h[0]
-    for (int k = 1; k < N_; ++k)
-      if (Z.GetStep(k) != Z.GetStep(0))
-        throw DeviceError(ALTRO_B200_ERR_UNSUPPORTED, "non-uniform time steps are not supported by the device solver (knot " +
-                                                          std::to_string(k) + ")");
-    SetStep(Z.GetStep(0));
+    {  // per-knot times and steps, exactly as the trajectory stores them
+      std::vector<float> t(static_cast<size_t>(N_) + 1), h(static_cast<size_t>(N_) + 1);
+      for (int k = 0; k <= N_; ++k) {
+        t[k] = static_cast<float>(Z.GetTime(k));
+        h[k] = Z.GetStep(k);
+      }
+      SetTimeGrid(t, h);
+    }
     Ensure();
     if (!explicit_x0_) {
       const VectorXd& x0 = prob_.GetInitialState();
@@ -416,7 +426,7 @@ class DeviceSolver {
     }
     Check(altro_b200_problem_set_model(p, model.model, model.params.data(), static_cast<int>(model.params.size())),
           "SetDynamics");
-    Check(altro_b200_problem_set_uniform_step(p, h_), "SetUniformStep");
+    Check(altro_b200_problem_set_steps(p, t_.data(), h_all_.data()), "SetUniformStep");
     for (int k = 0; k <= N_; ++k) {
       device::CostDesc c;
       if (!device::DescribeCost(*prob_.GetCostFunction(k), n_, m_, &c, &why))
@@ -479,7 +489,7 @@ class DeviceSolver {
   altro_b200_solver* solver_ = nullptr;
   std::vector<int> devices_;
   altro_b200_multi* multi_ = nullptr;
-  float h_ = 0.0f;
+  std::vector<float> t_, h_all_;
   bool have_step_ = false;
   double penalty_ = 0.0;
   bool have_penalty_ = false;

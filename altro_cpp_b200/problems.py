@@ -81,6 +81,14 @@ class ProblemSpec:
         self.h = float(np.float32(h))
         self.calls.append(("set_uniform_step", np.float32(h)))
 
+    def set_steps(self, t, h):
+        """Per-knot times and steps, float32 [N+1] each (Trajectory::SetTime / SetStep); h[N] is normally 0."""
+        t = np.ascontiguousarray(t, dtype=np.float32)
+        h = np.ascontiguousarray(h, dtype=np.float32)
+        assert t.shape == (self.N + 1,) and h.shape == (self.N + 1,)
+        self.h = None
+        self.calls.append(("set_steps", t, h))
+
     def set_cost(self, k0: int, k1: int, Q, R, H, q, r, c):
         self.calls.append(("set_cost", int(k0), int(k1), _colmajor(Q), _colmajor(R), _colmajor(H),
                            _f64(q), _f64(r), float(c)))
@@ -117,6 +125,10 @@ class ProblemSpec:
             elif name == "set_uniform_step":
                 fn.argtypes = [ctypes.c_void_p, ctypes.c_float]
                 rc = fn(handle, ctypes.c_float(float(args[0])))
+            elif name == "set_steps":
+                fp = ctypes.POINTER(ctypes.c_float)
+                fn.argtypes = [ctypes.c_void_p, fp, fp]
+                rc = fn(handle, args[0].ctypes.data_as(fp), args[1].ctypes.data_as(fp))
             elif name == "set_cost":
                 fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int] + [_dp] * 5 + [ctypes.c_double]
                 rc = fn(handle, args[0], args[1], *[_p(a) for a in args[2:7]], args[7])

@@ -116,6 +116,9 @@ int altro_b200_problem_set_model(altro_b200_problem* p, int model, const double*
                                  int nparams);
 /* Trajectory::SetUniformStep(h), altro/common/trajectory.hpp:122-130 */
 int altro_b200_problem_set_uniform_step(altro_b200_problem* p, float h);
+/* Per-knot times and steps (Trajectory::SetTime / SetStep, altro/common/trajectory.hpp:119-120): t[N+1], h[N+1]
+ * as the trajectory stores them (h[N] is the terminal knot's, normally 0); h[k] > 0 for k < N. */
+int altro_b200_problem_set_steps(altro_b200_problem* p, const float* t, const float* h);
 /* SetCostFunction(QuadraticCost(Q,R,H,q,r,c), k) for k0 <= k < k1
  * (altro/problem/problem.hpp:113-121; examples/quadratic_cost.hpp:12-27) */
 int altro_b200_problem_set_cost(altro_b200_problem* p, int k0, int k1, const double* Q,

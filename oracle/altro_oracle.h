@@ -46,6 +46,7 @@ int altro_oracle_problem_create(int n, int m, int N, void** out);
 void altro_oracle_problem_destroy(void* p);
 int altro_oracle_problem_set_model(void* p, int kind, const double* params, int nparams);
 int altro_oracle_problem_set_uniform_step(void* p, float h);
+int altro_oracle_problem_set_steps(void* p, const float* t, const float* h);
 int altro_oracle_problem_set_cost(void* p, int k0, int k1, const double* Q, const double* R,
                                   const double* H, const double* q, const double* r, double c);
 int altro_oracle_problem_add_goal(void* p, int k, const double* xf);

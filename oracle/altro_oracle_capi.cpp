@@ -242,6 +242,14 @@ int altro_oracle_problem_set_uniform_step(void* p, float h) {
   static_cast<Problem*>(p)->SetUniformStep(h);
   return 0;
 }
+int altro_oracle_problem_set_steps(void* p, const float* t, const float* h) {
+  Problem& P = *static_cast<Problem*>(p);
+  for (int k = 0; k <= P.N; ++k) {  // Trajectory::SetTime / SetStep per knot, altro/common/trajectory.hpp:119-120
+    P.t[k] = t[k];
+    P.h[k] = h[k];
+  }
+  return 0;
+}
 int altro_oracle_problem_set_cost(void* p, int k0, int k1, const double* Q, const double* R,
                                   const double* H, const double* q, const double* r, double c) {
   Problem& P = *static_cast<Problem*>(p);

@@ -275,6 +275,32 @@ void TestUnicycleILQR() {
   EXPECT(g.GetFeedbackGain().rows() == 2 && g.GetFeedbackGain().cols() == 3);
 }
 
+// a trajectory with per-knot steps (Trajectory::SetStep / SetTime) is solved on its own time grid
+void TestNonUniformSteps() {
+  UnicycleProblem def;
+  auto uniform = def.MakeALSolver();
+  uniform.Solve();
+  const double J_uniform = uniform.GetiLQRSolver().Cost();
+
+  auto solver = def.MakeALSolver();
+  auto Z = solver.GetiLQRSolver().GetTrajectory();
+  const int N = Z->NumSegments();
+  float t = 0.0F;
+  for (int k = 0; k <= N; ++k) {  // fine steps first, coarse steps last; same final time to within a few percent
+    const float h = k < N ? Z->GetStep(0) * (0.5F + static_cast<float>(k) / static_cast<float>(N)) : 0.0F;
+    Z->SetTime(k, t);
+    Z->SetStep(k, h);
+    t += h;
+  }
+  EXPECT(Z->CheckTimeConsistency());
+  solver.Solve();
+  EXPECT(solver.GetStatus() == SolverStatus::kSolved);
+  EXPECT(solver.MaxViolation() < 1e-4);
+  const double J = solver.GetiLQRSolver().Cost();
+  EXPECT(std::fabs(J - J_uniform) > 1e-6 * J_uniform);  // a different discretisation, a different optimum
+  EXPECT(std::fabs(J - J_uniform) < 0.5 * J_uniform);
+}
+
 // test/augmented_lagrangian/auglag_test.cpp:326-380
 void TestUnicycleAugLag() {
   UnicycleProblem def;
@@ -402,6 +428,7 @@ int main(int argc, char* argv[]) {
     } else {
       TestUnicycleILQR();
       TestUnicycleAugLag();
+      TestNonUniformSteps();
       TestThreeObstacles();
       TestTripleIntegrator();
     }

@@ -602,6 +602,27 @@ def test_large_state_kernels_agree_on_a_ragged_batch(gpu):
         assert e <= tol[k], (k, e)
 
 
+def test_non_uniform_time_steps(gpu, oracle):
+    """Per-knot times and steps (Trajectory::SetTime / SetStep, altro/common/trajectory.hpp:119-120): a grid that is
+    fine near the start and coarse towards the end, same discrete path and trajectories as the oracle."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    N = spec.N
+    h = np.linspace(0.02, 0.08, N + 1).astype(np.float32)   # mean ~0.05 like the uniform problem
+    h[N] = 0.0
+    t = np.zeros(N + 1, dtype=np.float32)
+    for k in range(N):
+        t[k + 1] = np.float32(t[k] + h[k])
+    spec.set_steps(t, h)
+    X0 = P.perturbed_initial_states(spec, 40, P.UNICYCLE_X0_SCALE)
+    errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, al=True, max_mismatch_frac=0.0)
+    assert errs["X"] <= 1e-8 and errs["cost"] <= 1e-8, errs
+    # and it is a different problem from the uniform one
+    uni = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    s = gpu.BatchSolver(uni, 40)
+    s.set_inputs(X0); s.solve_al()
+    assert np.abs(s.results()["cost"] - r["cost"]).max() > 1e-3
+
+
 def test_solver_stats_history_against_the_oracle(gpu, oracle):
     """SolverStats vectors (altro/common/solver_stats.hpp:54-61) recorded on the device, row by row against the
     oracle's Log()/NewIteration() restatement: cost, alpha, improvement ratio, gradient, cost decrease,
