@@ -58,6 +58,7 @@ class DeviceSolver {
   int m() const { return m_; }
   int NumSegments() const { return N_; }
   int Batch() const { return B_; }
+  bool UsesConstraints() const { return use_constraints_; }
   SolverOptions& GetOptions() { return stats_.GetOptions(); }
   SolverStats& GetStats() { return stats_; }
 
@@ -165,7 +166,23 @@ class DeviceSolver {
     kSolveILQR,
     kSolveAL
   };
+  // Duals edited on the host (GetALCost(k)->Get...Constraints()[i]->GetDuals() = ...) reach the device right
+  // before the next device phase: the view hands out a buffer and registers it here.
+  void PushDualsBeforeNextRun(int k, int row0, std::shared_ptr<VectorXd> values) {
+    pending_duals_.push_back({k, row0, std::move(values)});
+  }
+  void FlushPendingDuals() {
+    if (pending_duals_.empty() || Sharded() || !solver_) return;
+    std::vector<PendingDuals> todo;
+    todo.swap(pending_duals_);
+    for (const PendingDuals& e : todo) {
+      std::vector<double> all = Duals(e.k, 0);
+      for (int i = 0; i < e.values->size(); ++i) all.at(static_cast<size_t>(e.row0 + i)) = (*e.values)(i);
+      Check(altro_b200_solver_set_duals_host(solver_, e.k, all.data(), static_cast<int>(all.size()), nullptr), "GetDuals");
+    }
+  }
   void Run(Phase ph) {
+    FlushPendingDuals();
     if (Sharded()) {
       if (ph != kSolveAL) throw DeviceError(ALTRO_B200_ERR_UNSUPPORTED, "a batch sharded over several GPUs supports whole solves only");
       if (!multi_) throw DeviceError(ALTRO_B200_ERR_STATE, "SetTrajectory must be called before this method");
@@ -483,6 +500,11 @@ class DeviceSolver {
 
   problem::Problem prob_;  // shares the functors and the initial-state pointer with the caller
   int n_, m_, N_, B_, device_;
+  struct PendingDuals {
+    int k, row0;
+    std::shared_ptr<VectorXd> values;
+  };
+  std::vector<PendingDuals> pending_duals_;
   bool use_constraints_;
   bool has_constraints_ = false, history_ = false;
   int history_rows_ = 0;

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "altro/common/threadpool.hpp"
+#include "altro/augmented_lagrangian/al_cost.hpp"
 #include "altro/device_solver.hpp"
 #include "altro/ilqr/knot_point_function_type.hpp"
 
@@ -75,26 +76,9 @@ class iLQR {
   // UpdateExpansions() / BackwardPass().  Refreshed from the device on every call.
   KnotPointFunctions<n, m>& GetKnotPointFunction(int k) {
     ALTRO_ASSERT(k >= 0 && k <= N_, "Invalid knot point index.");
-    KnotPointFunctions<n, m>& kpf = *knotpoints_.at(k);
-    detail::DeviceSolver& c = Core();
-    if (!c.Ready()) return kpf;
-    const int nn = c.n(), mm = c.m();
-    if (k < N_) {
-      std::vector<double> K, d;
-      c.Gains(0, &K, &d);
-      for (int j = 0; j < nn; ++j)
-        for (int i = 0; i < mm; ++i) kpf.GetFeedbackGain()(i, j) = K[(static_cast<size_t>(k) * nn + j) * mm + i];
-      for (int i = 0; i < mm; ++i) kpf.GetFeedforwardGain()(i) = d[static_cast<size_t>(k) * mm + i];
-    }
-    MatrixXd A, B;
-    CostExpansion<n, m>& e = kpf.GetCostExpansion();
-    if (c.TryExpansion(k, 0, &A, &B, &e.dxdx(), &e.dxdu(), &e.dudu(), &e.dx(), &e.du())) {
-      MatrixXd& J = kpf.GetDynamicsExpansion().GetJacobian();
-      J.topLeftCorner(nn, nn) = A;
-      J.topRightCorner(nn, mm) = B;
-    }
-    c.TryCostToGo(k, 0, &kpf.GetCostToGoHessian(), &kpf.GetCostToGoGradient());
-    return kpf;
+    handed_out_.at(k) = 1;  // a reference the caller may keep: refreshed again after every device phase
+    RefreshKnotPoint(k);
+    return *knotpoints_.at(k);
   }
 
   // The batch axis replaces the thread pool: one launch covers every knot point.  These keep the
@@ -131,6 +115,7 @@ class iLQR {
     Core().Download(Z_.get());
     Core().Pull();
     Core().PullHistory(/*al=*/false);
+    RefreshHandedOut();
   }
   void Rollout() {
     Require();
@@ -138,17 +123,23 @@ class iLQR {
     Core().Run(detail::DeviceSolver::kRollout);
     Core().Download(Z_.get());
   }
+  // The trajectory is shared with the caller (ilqr.hpp:226-235 there), who may have edited it in place: the phases
+  // that read it as their input take the host copy to the device first.
   double Cost() {
+    if (Z_) Core().Upload(*Z_);
     Core().Run(detail::DeviceSolver::kCost);
     return Core().Pull().cost[0];
   }
   double Cost(const Trajectory<n, m>& Z) {
     Core().Upload(Z);
-    return Cost();
+    Core().Run(detail::DeviceSolver::kCost);
+    return Core().Pull().cost[0];
   }
   void UpdateExpansions() {
     SyncThreadBookkeeping();
+    if (Z_) Core().Upload(*Z_);
     Core().Run(detail::DeviceSolver::kUpdateExpansions);
+    RefreshHandedOut();
   }
   // one launch covers every knot point; a block request runs the same launch (ilqr.hpp:670-677 there)
   void UpdateExpansionsBlock(int start, int stop) {
@@ -156,7 +147,10 @@ class iLQR {
     ALTRO_UNUSED(stop);
     Core().Run(detail::DeviceSolver::kUpdateExpansions);
   }
-  void BackwardPass() { Core().Run(detail::DeviceSolver::kBackwardPass); }
+  void BackwardPass() {
+    Core().Run(detail::DeviceSolver::kBackwardPass);
+    RefreshHandedOut();
+  }
   void ForwardPass() {
     Require();
     Core().Run(detail::DeviceSolver::kForwardPass);
@@ -189,11 +183,44 @@ class iLQR {
     ALTRO_ASSERT(Z_ != nullptr, "Invalid trajectory pointer. May be uninitialized.");
     if (!Z_) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
   }
+  void RefreshKnotPoint(int k) {
+    KnotPointFunctions<n, m>& kpf = *knotpoints_.at(k);
+    detail::DeviceSolver& c = Core();
+    if (!c.Ready()) return;
+    const int nn = c.n(), mm = c.m();
+    if (k < N_) {
+      std::vector<double> K, d;
+      c.Gains(0, &K, &d);
+      for (int j = 0; j < nn; ++j)
+        for (int i = 0; i < mm; ++i) kpf.GetFeedbackGain()(i, j) = K[(static_cast<size_t>(k) * nn + j) * mm + i];
+      for (int i = 0; i < mm; ++i) kpf.GetFeedforwardGain()(i) = d[static_cast<size_t>(k) * mm + i];
+    }
+    MatrixXd A, B;
+    CostExpansion<n, m>& e = kpf.GetCostExpansion();
+    if (c.TryExpansion(k, 0, &A, &B, &e.dxdx(), &e.dxdu(), &e.dudu(), &e.dx(), &e.du())) {
+      MatrixXd& J = kpf.GetDynamicsExpansion().GetJacobian();
+      J.topLeftCorner(nn, nn) = A;
+      J.topRightCorner(nn, mm) = B;
+    }
+    c.TryCostToGo(k, 0, &kpf.GetCostToGoHessian(), &kpf.GetCostToGoGradient());
+  }
+  // references returned by GetKnotPointFunction stay current across device phases, like the reference's (which
+  // point at the solver's own storage); knot points nobody asked for are not fetched
+  void RefreshHandedOut() {
+    for (int k = 0; k <= N_; ++k)
+      if (handed_out_[k]) RefreshKnotPoint(k);
+  }
   void MakeKnotPoints() {
+    handed_out_.assign(static_cast<size_t>(N_) + 1, 0);
     knotpoints_.clear();
     const problem::Problem& prob = core_->GetProblem();
-    for (int k = 0; k <= N_; ++k)
-      knotpoints_.emplace_back(std::make_unique<KnotPointFunctions<n, m>>(prob.GetDynamics(k), prob.GetCostFunction(k)));
+    // For an augmented-Lagrangian problem the cost object of a knot point is its ALCost (as in the reference, where
+    // BuildAugLagProblem wraps every cost): GetCostFunPtr() then gives access to the duals and penalty of the knot.
+    for (int k = 0; k <= N_; ++k) {
+      std::shared_ptr<problem::CostFunction> cost = prob.GetCostFunction(k);
+      if (core_->UsesConstraints()) cost = std::make_shared<augmented_lagrangian::ALCost<n, m>>(core_, k);
+      knotpoints_.emplace_back(std::make_unique<KnotPointFunctions<n, m>>(prob.GetDynamics(k), cost));
+    }
   }
   void SyncThreadBookkeeping() {
     nthreads_launched_ = core_ ? core_->GetOptions().NumThreads() : 1;
@@ -214,6 +241,7 @@ class iLQR {
   std::shared_ptr<detail::DeviceSolver> core_;
   std::shared_ptr<Trajectory<n, m>> Z_;
   std::vector<std::unique_ptr<KnotPointFunctions<n, m>>> knotpoints_;
+  std::vector<char> handed_out_;  // knot points whose KnotPointFunctions reference was given to the caller
   std::vector<int> work_inds_ = {0, 1};
   bool custom_work_assignment_ = false;
   int nthreads_launched_ = 0;

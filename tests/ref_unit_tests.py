@@ -23,7 +23,7 @@ EXAMPLE_SOURCES = ["examples/unicycle.cpp", "examples/triple_integrator.cpp", "e
 # Unit tests of the reference that exercise only host-side classes the mirror re-implements: run on the CPU.
 # Not listed: common/trajectory_test.cpp (its fixture reads U[N], one past the end of a std::vector — harmless with
 # Eigen's in-place fixed-size storage, not with the heap-backed stand-in); utils/benchmarking_test.cpp,
-# constraints/constraints_test.cpp, ilqr/ilqr_test.cpp, ilqr/knot_point_functions_test.cpp and
+# constraints/constraints_test.cpp, ilqr/knot_point_functions_test.cpp and
 # augmented_lagrangian/auglag_test.cpp (they test classes internal to the reference's CPU solver —
 # ConstraintValues, ALCost construction, KnotPointFunctions arithmetic — that have no host counterpart here: that
 # arithmetic lives on the device and is pinned by tests/test_oracle_golden.py and tests/test_gpu_parity.py).
@@ -34,7 +34,7 @@ HOST_TESTS = ["common/knotpoint_test.cpp", "common/functionbase_test.cpp", "comm
               "utils/derivative_checker_test.cpp", "ilqr/cost_expansion_test.cpp", "ilqr/dynamics_expansion_test.cpp"]
 # Tests that build solvers and solve: compiled here, run on the GPU box (the reference's own golden values —
 # iteration counts, costs, alpha, gains — checked by the reference's own assertions, on the device).
-DEVICE_TESTS = ["ilqr/unicycle_ilqr_test.cpp", "ilqr/ilqr_class_test.cpp", "examples/example_unicycle_test.cpp",
+DEVICE_TESTS = ["ilqr/unicycle_ilqr_test.cpp", "ilqr/ilqr_test.cpp", "ilqr/ilqr_class_test.cpp", "examples/example_unicycle_test.cpp",
                 "examples/example_triple_integrator_test.cpp"]
 
 
