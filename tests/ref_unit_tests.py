@@ -21,13 +21,11 @@ EXAMPLE_SOURCES = ["examples/unicycle.cpp", "examples/triple_integrator.cpp", "e
                    "examples/problems/unicycle.cpp", "examples/problems/triple_integrator.cpp"]
 
 # Unit tests of the reference that exercise only host-side classes the mirror re-implements: run on the CPU.
-# Not listed: common/trajectory_test.cpp (its fixture reads U[N], one past the end of a std::vector — harmless with
-# Eigen's in-place fixed-size storage, not with the heap-backed stand-in); utils/benchmarking_test.cpp,
-# constraints/constraints_test.cpp, ilqr/knot_point_functions_test.cpp and
+# Not listed: utils/benchmarking_test.cpp, constraints/constraints_test.cpp, ilqr/knot_point_functions_test.cpp and
 # augmented_lagrangian/auglag_test.cpp (they test classes internal to the reference's CPU solver —
 # ConstraintValues, ALCost construction, KnotPointFunctions arithmetic — that have no host counterpart here: that
 # arithmetic lives on the device and is pinned by tests/test_oracle_golden.py and tests/test_gpu_parity.py).
-HOST_TESTS = ["common/knotpoint_test.cpp", "common/functionbase_test.cpp", "common/solver_options_test.cpp",
+HOST_TESTS = ["common/knotpoint_test.cpp", "common/trajectory_test.cpp", "common/functionbase_test.cpp", "common/solver_options_test.cpp",
               "common/solver_logging_test.cpp", "common/timer_test.cpp", "common/threadpool_test.cpp",
               "problem/problem_test.cpp", "problem/dynamics_test.cpp", "problem/costfunction_test.cpp",
               "problem/quadratic_cost_test.cpp", "problem/unicycle_test.cpp", "problem/triple_integrator_test.cpp",

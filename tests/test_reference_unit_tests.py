@@ -3,7 +3,7 @@ mirror: compiled where they lie under /root/reference with the mirror's headers,
 GoogleTest stand-in (tests/cpp/gtest_standin), linked with libaltro_b200.so (tests/ref_unit_tests.py).
 
 * host-side classes (KnotPoint, Problem, cost / dynamics functors, derivative checks, expansions, thread pool, timer,
-  logger, options): 15 test programs, run here on the CPU;
+  logger, options): 16 test programs, run here on the CPU;
 * solver tests (unicycle_ilqr_test, ilqr_test, ilqr_class_test, example_unicycle_test, example_triple_integrator_test): built
   here, run on the GPU box from the executables that travel with the snapshot — the reference's golden iteration
   counts, costs, step lengths and gains, asserted by the reference's own code, on the device.
