@@ -1,151 +1,209 @@
-// altro/augmented_lagrangian/al_cost.hpp (B200 host mirror) — ALCost<n,m>, the per-knot object
-// behind AugmentedLagrangianiLQR::GetALCost(k) (altro/augmented_lagrangian/al_cost.hpp:37 there).
+// altro/augmented_lagrangian/al_cost.hpp (B200 host mirror) — ALCost<n,m>: the cost of one knot point plus the
+// augmented-Lagrangian terms of its constraints (altro/augmented_lagrangian/al_cost.hpp:37 there), and the object
+// behind AugmentedLagrangianiLQR::GetALCost(k).
 //
-// In the reference this object evaluates cost + augmented-Lagrangian terms and owns the duals and
-// penalties of the knot's constraints (ConstraintValues, altro/constraints/constraint_values.hpp:24).
-// Here those live on the device (csrc/device.cuh al_value / al_expansion; duals in LAM, one penalty
-// per instance) and this is the host-side view of them: constraint counts, duals, penalty, constraint
-// values and violations of the current trajectory, fetched from the device on request.
+// The multipliers and penalties belong to its ConstraintValues (altro/constraints/constraint_values.hpp).  Built
+// from a problem (or empty, then filled with SetCostFunction / Set...Constraints) it is a self-contained host
+// object: Evaluate / Gradient / Hessian at a point (x, u) the caller passes.  Built by a solver it is bound to
+// that solver's device state: the same calls use the device's multipliers and penalty, MaxViolation() and the
+// constraint getters report the solver's current trajectory.  The solve itself never comes through here — the
+// kernels add these terms (csrc/device.cuh al_value / al_expansion).
 #pragma once
 
+#include <algorithm>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "altro/constraints/constraint.hpp"
+#include "altro/constraints/constraint_values.hpp"
 #include "altro/device_solver.hpp"
 #include "altro/problem/costfunction.hpp"
+#include "altro/problem/problem.hpp"
 
 namespace altro {
 namespace augmented_lagrangian {
 
-// one constraint of one knot (the reference's ConstraintValues<n, m, ConType>)
-class ConstraintValuesView {
- public:
-  ConstraintValuesView(std::shared_ptr<detail::DeviceSolver> core, int k, int row0, int p, std::string label, std::string type,
-                       bool equality)
-      : core_(std::move(core)), k_(k), row0_(row0), p_(p), label_(std::move(label)), type_(std::move(type)),
-        equality_(equality) {}
-  int OutputDimension() const { return p_; }
-  std::string GetLabel() const { return label_; }
-  VectorXd GetDuals() const { return Slice(core_->Duals(k_, 0)); }
-  // writable: the returned vector starts as the device's duals and is sent back right before the next device
-  // phase (every instance of a batched solver receives the same values)
-  VectorXd& GetDuals() {
-    if (!edited_) edited_ = std::make_shared<VectorXd>();
-    *edited_ = Slice(core_->Duals(k_, 0));
-    core_->PushDualsBeforeNextRun(k_, row0_, edited_);
-    return *edited_;
-  }
-  // the device keeps ONE penalty per instance, uniform over all constraints: this sets it
-  void SetPenalty(double rho) { core_->SetPenalty(rho); }
-  VectorXd GetConstraintValue() const { return Slice(core_->ConstraintValues(k_, 0)); }
-  // the penalty is one scalar per instance on the device, uniform over the rows
-  VectorXd GetPenalty() const { return VectorXd::Constant(p_, core_->MaxPenalty(0)); }
-  double MaxPenalty() const { return core_->MaxPenalty(0); }
-  // c - Pi_K(c): |c| for equalities, max(0, c) for inequalities (constraint_values.hpp:216-221 there)
-  VectorXd GetViolation() const {
-    VectorXd v = GetConstraintValue();
-    for (int i = 0; i < p_; ++i) v(i) = equality_ ? v(i) : (v(i) > 0.0 ? v(i) : 0.0);
-    return v;
-  }
-  double MaxViolation() const {
-    const VectorXd v = GetViolation();
-    double r = 0.0;
-    for (int i = 0; i < p_; ++i) r = std::max(r, std::fabs(v(i)));
-    return r;
-  }
-  constraints::ConstraintInfo GetConstraintInfo() const { return constraints::ConstraintInfo{label_, k_, GetViolation(), type_}; }
-
- private:
-  VectorXd Slice(const std::vector<double>& all) const {
-    VectorXd out = VectorXd::Zero(p_);
-    for (int i = 0; i < p_; ++i) out(i) = all.at(static_cast<size_t>(row0_ + i));
-    return out;
-  }
-  std::shared_ptr<detail::DeviceSolver> core_;
-  int k_, row0_, p_;
-  std::string label_, type_;
-  bool equality_;
-  std::shared_ptr<VectorXd> edited_;
-};
-
-}  // namespace augmented_lagrangian
-
-namespace constraints {
-// the reference's name and template signature for the per-constraint state of an ALCost
-// (altro/constraints/constraint_values.hpp:24 there); here a typed handle on the device-side state
-template <int n, int m, class ConType>
-class ConstraintValues : public augmented_lagrangian::ConstraintValuesView {
- public:
-  using augmented_lagrangian::ConstraintValuesView::ConstraintValuesView;
-};
-}  // namespace constraints
-
-namespace augmented_lagrangian {
-
-// As a CostFunction this object evaluates the PLAIN cost of its knot (it forwards to the user's functor): the
-// augmented-Lagrangian terms it stands for are added on the device (csrc/device.cuh al_value / al_expansion),
-// and iLQR::Cost() / GetCostExpansion() of an AL problem report them from there.
 template <int n, int m>
 class ALCost : public problem::CostFunction {
-  using EqValues = constraints::ConstraintValues<n, m, constraints::Equality>;
-  using IneqValues = constraints::ConstraintValues<n, m, constraints::Inequality>;
-
  public:
-  ALCost(std::shared_ptr<detail::DeviceSolver> core, int k) : core_(std::move(core)), k_(k) {
-    const problem::Problem& prob = core_->GetProblem();
-    base_ = prob.GetCostFunction(k);
-    int row = 0;  // ALCost order: equalities, then inequalities (al_cost.hpp:264-273 there)
-    for (const auto& con : prob.GetEqualityConstraints()[k]) {
-      eq_.emplace_back(std::make_shared<EqValues>(core_, k, row, con->OutputDimension(), con->GetLabel(),
-                                                  con->GetConstraintType(), true));
-      row += con->OutputDimension();
-    }
-    for (const auto& con : prob.GetInequalityConstraints()[k]) {
-      ineq_.emplace_back(std::make_shared<IneqValues>(core_, k, row, con->OutputDimension(), con->GetLabel(),
-                                                      con->GetConstraintType(), false));
-      row += con->OutputDimension();
-    }
-    p_ = row;
+  template <class ConType>
+  using ConstraintValueVec = std::vector<std::shared_ptr<constraints::ConstraintValues<n, m, ConType>>>;
+
+  // no cost, no constraints yet
+  ALCost(int state_dim, int control_dim) : n_(state_dim), m_(control_dim) { Scratch(); }
+  // cost and constraints of knot k of `prob`; multipliers zero, penalties one
+  ALCost(const problem::Problem& prob, int k) : n_(prob.GetDynamics(k)->StateDimension()),
+                                                m_(prob.GetDynamics(k)->ControlDimension()), k_(k) {
+    Scratch();
+    SetCostFunction(prob.GetCostFunction(k));
+    SetEqualityConstraints(prob.GetEqualityConstraints().at(k).begin(), prob.GetEqualityConstraints().at(k).end());
+    SetInequalityConstraints(prob.GetInequalityConstraints().at(k).begin(), prob.GetInequalityConstraints().at(k).end());
   }
-  int NumConstraints() const { return p_; }
-  const std::vector<std::shared_ptr<EqValues>>& GetEqualityConstraints() const { return eq_; }
-  const std::vector<std::shared_ptr<IneqValues>>& GetInequalityConstraints() const { return ineq_; }
-  std::shared_ptr<problem::CostFunction> GetCostFunction() const { return base_; }
-  double MaxViolation() const {
-    double r = 0.0;
-    for (const auto& c : eq_) r = std::max(r, c->MaxViolation());
-    for (const auto& c : ineq_) r = std::max(r, c->MaxViolation());
-    return r;
-  }
-  double MaxPenalty() const { return p_ > 0 ? core_->MaxPenalty(0) : 0.0; }
-  void GetConstraintInfo(std::vector<constraints::ConstraintInfo>* coninfo) const {
-    for (const auto& c : eq_) coninfo->emplace_back(c->GetConstraintInfo());
-    for (const auto& c : ineq_) coninfo->emplace_back(c->GetConstraintInfo());
+  // knot k of a device solver: multipliers, penalty and constraint values are the device's
+  ALCost(std::shared_ptr<detail::DeviceSolver> core, int k) : ALCost(core->GetProblem(), k) {
+    core_ = std::move(core);
+    int row = 0;  // ALCost row order: equalities, then inequalities
+    for (auto& v : eq_) {
+      v->BindDevice(core_, k, row);
+      row += v->OutputDimension();
+    }
+    for (auto& v : ineq_) {
+      v->BindDevice(core_, k, row);
+      row += v->OutputDimension();
+    }
   }
 
-  // ---- CostFunction interface: the plain cost of this knot
+  // ---- contents
+  void SetCostFunction(const std::shared_ptr<problem::CostFunction>& costfun) {
+    ALTRO_ASSERT(costfun != nullptr, "Cost function cannot be a nullptr.");
+    costfun_ = costfun;
+  }
+  template <class Iterator>
+  void SetEqualityConstraints(const Iterator& begin, const Iterator& end) {
+    Wrap(begin, end, &eq_);
+  }
+  template <class Iterator>
+  void SetInequalityConstraints(const Iterator& begin, const Iterator& end) {
+    Wrap(begin, end, &ineq_);
+  }
+  std::shared_ptr<problem::CostFunction> GetCostFunction() { return costfun_; }
+  ConstraintValueVec<constraints::Equality>& GetEqualityConstraints() { return eq_; }
+  ConstraintValueVec<constraints::Inequality>& GetInequalityConstraints() { return ineq_; }
+  int NumConstraints() {
+    int rows = 0;
+    for (const auto& v : eq_) rows += v->OutputDimension();
+    for (const auto& v : ineq_) rows += v->OutputDimension();
+    return rows;
+  }
+  template <class ConType>
+  int NumConstraintFunctions() {
+    return static_cast<int>(Of<ConType>().size());
+  }
+  void GetConstraintInfo(std::vector<constraints::ConstraintInfo>* coninfo) {
+    for (auto& v : eq_) coninfo->emplace_back(v->GetConstraintInfo());
+    for (auto& v : ineq_) coninfo->emplace_back(v->GetConstraintInfo());
+  }
+
+  // ---- penalties: one constraint function, or all of one cone
+  template <class ConType>
+  void SetPenalty(const double rho, const int i) {
+    ALTRO_ASSERT(0 <= i && i < NumConstraintFunctions<ConType>(), "Invalid constraint index.");
+    Of<ConType>().at(i)->SetPenalty(rho);
+  }
+  template <class ConType>
+  void SetPenalty(const double rho) {
+    for (auto& v : Of<ConType>()) v->SetPenalty(rho);
+  }
+  template <class ConType>
+  void SetPenaltyScaling(const double phi, const int i) {
+    ALTRO_ASSERT(0 <= i && i < NumConstraintFunctions<ConType>(), "Invalid constraint index.");
+    Of<ConType>().at(i)->SetPenaltyScaling(phi);
+  }
+  template <class ConType>
+  void SetPenaltyScaling(const double phi) {
+    for (auto& v : Of<ConType>()) v->SetPenaltyScaling(phi);
+  }
+
+  // ---- CostFunction interface: cost + sum of the constraints' augmented-Lagrangian terms at (x, u)
   using problem::CostFunction::Gradient;
   using problem::CostFunction::Hessian;
-  int StateDimension() const override { return base_->StateDimension(); }
-  int ControlDimension() const override { return base_->ControlDimension(); }
-  double Evaluate(const VectorXdRef& x, const VectorXdRef& u) override { return base_->Evaluate(x, u); }
+  int StateDimension() const override { return n_; }
+  int ControlDimension() const override { return m_; }
+  double Evaluate(const VectorXdRef& x, const VectorXdRef& u) override {
+    ALTRO_ASSERT(costfun_ != nullptr, "Cost function must be set before evaluating.");
+    double J = costfun_->Evaluate(x, u);
+    for (auto& v : eq_) J += v->AugLag(x, u);
+    for (auto& v : ineq_) J += v->AugLag(x, u);
+    return J;
+  }
   void Gradient(const VectorXdRef& x, const VectorXdRef& u, Eigen::Ref<VectorXd> dx, Eigen::Ref<VectorXd> du) override {
-    base_->Gradient(x, u, dx, du);
+    ALTRO_ASSERT(costfun_ != nullptr, "Cost function must be set before evaluating.");
+    costfun_->Gradient(x, u, dx, du);
+    auto add = [&](auto& v) {
+      v->AugLagGradient(x, u, gx_, gu_);
+      for (int i = 0; i < n_; ++i) dx(i) += gx_(i);
+      for (int i = 0; i < m_; ++i) du(i) += gu_(i);
+    };
+    for (auto& v : eq_) add(v);
+    for (auto& v : ineq_) add(v);
   }
   void Hessian(const VectorXdRef& x, const VectorXdRef& u, Eigen::Ref<MatrixXd> dxdx, Eigen::Ref<MatrixXd> dxdu,
                Eigen::Ref<MatrixXd> dudu) override {
-    base_->Hessian(x, u, dxdx, dxdu, dudu);
+    ALTRO_ASSERT(costfun_ != nullptr, "Cost function must be set before evaluating.");
+    costfun_->Hessian(x, u, dxdx, dxdu, dudu);
+    auto add = [&](auto& v) {
+      v->AugLagHessian(x, u, hxx_, hxu_, huu_, /*full_newton=*/false);
+      for (int i = 0; i < n_; ++i) {
+        for (int j = 0; j < n_; ++j) dxdx(i, j) += hxx_(i, j);
+        for (int j = 0; j < m_; ++j) dxdu(i, j) += hxu_(i, j);
+      }
+      for (int i = 0; i < m_; ++i)
+        for (int j = 0; j < m_; ++j) dudu(i, j) += huu_(i, j);
+    };
+    for (auto& v : eq_) add(v);
+    for (auto& v : ineq_) add(v);
+  }
+
+  // ---- outer-loop steps of a standalone object (a solver updates all knot points in one launch)
+  void UpdateDuals() {
+    for (auto& v : eq_) v->UpdateDuals();
+    for (auto& v : ineq_) v->UpdateDuals();
+  }
+  void UpdatePenalties() {
+    for (auto& v : eq_) v->UpdatePenalties();
+    for (auto& v : ineq_) v->UpdatePenalties();
+  }
+  void ResetDualVariables() {
+    for (auto& v : eq_) v->ResetDualVariables();
+    for (auto& v : ineq_) v->ResetDualVariables();
+  }
+  template <int norm = Eigen::Infinity>
+  double MaxViolation() {
+    double worst = 0.0;  // the norm over constraints is taken as a maximum for every `norm`, as there
+    for (auto& v : eq_) worst = std::max(worst, v->template MaxViolation<norm>());
+    for (auto& v : ineq_) worst = std::max(worst, v->template MaxViolation<norm>());
+    return worst;
+  }
+  double MaxPenalty() {
+    double worst = 0.0;
+    for (auto& v : eq_) worst = std::max(worst, v->MaxPenalty());
+    for (auto& v : ineq_) worst = std::max(worst, v->MaxPenalty());
+    return worst;
   }
 
  private:
+  template <class Iterator, class ConType>
+  void Wrap(const Iterator& begin, const Iterator& end, ConstraintValueVec<ConType>* values) {
+    ALTRO_ASSERT(values != nullptr, "Must provide a pointer to a valid collection.");
+    values->clear();
+    for (Iterator it = begin; it != end; ++it)
+      values->emplace_back(std::make_shared<constraints::ConstraintValues<n, m, ConType>>(n_, m_, *it));
+  }
+  // the collection of one cone, selected by type
+  ConstraintValueVec<constraints::Equality>& Pick(const constraints::Equality*) { return eq_; }
+  ConstraintValueVec<constraints::Inequality>& Pick(const constraints::Inequality*) { return ineq_; }
+  template <class ConType>
+  ConstraintValueVec<ConType>& Of() {
+    return Pick(static_cast<const ConType*>(nullptr));
+  }
+  void Scratch() {
+    gx_ = VectorXd::Zero(n_);
+    gu_ = VectorXd::Zero(m_);
+    hxx_ = MatrixXd::Zero(n_, n_);
+    hxu_ = MatrixXd::Zero(n_, m_);
+    huu_ = MatrixXd::Zero(m_, m_);
+  }
+
+  int n_, m_;
+  int k_ = 0;
+  std::shared_ptr<problem::CostFunction> costfun_;
+  ConstraintValueVec<constraints::Equality> eq_;
+  ConstraintValueVec<constraints::Inequality> ineq_;
+  VectorXd gx_, gu_;       // one constraint's contribution, before it is added
+  MatrixXd hxx_, hxu_, huu_;
   std::shared_ptr<detail::DeviceSolver> core_;
-  std::shared_ptr<problem::CostFunction> base_;
-  int k_;
-  int p_ = 0;
-  std::vector<std::shared_ptr<EqValues>> eq_;
-  std::vector<std::shared_ptr<IneqValues>> ineq_;
 };
 
 }  // namespace augmented_lagrangian

@@ -47,10 +47,10 @@ class AugmentedLagrangianiLQR {
 
   void SetTrajectory(std::shared_ptr<Trajectory<n, m>> traj) { ilqr_solver_.SetTrajectory(std::move(traj)); }
   ilqr::iLQR<n, m>& GetiLQRSolver() { return ilqr_solver_; }
-  SolverOptions& GetOptions() { return core_->GetOptions(); }
-  SolverStats& GetStats() { return core_->GetStats(); }
-  SolverStatus GetStatus() { return static_cast<SolverStatus>(core_->Pull().status[0]); }
-  int NumSegments() const { return core_->NumSegments(); }
+  SolverOptions& GetOptions() { return Initialized().GetOptions(); }
+  SolverStats& GetStats() { return Initialized().GetStats(); }
+  SolverStatus GetStatus() { return static_cast<SolverStatus>(Initialized().Pull().status[0]); }
+  int NumSegments() const { return ilqr_solver_.NumSegments(); }
 
   void SetPenalty(double rho) { core_->SetPenalty(rho); }
   void SetPenaltyScaling(double phi) { core_->SetPenaltyScaling(phi); }
@@ -82,8 +82,8 @@ class AugmentedLagrangianiLQR {
   }
   double GetMaxViolation() { return MaxViolation(); }
   double GetMaxPenalty() { return core_->MaxPenalty(0); }
-  int NumConstraints(int k) const { return core_->GetProblem().NumConstraints(k); }
-  int NumConstraints() const { return core_->GetProblem().NumConstraints(); }
+  int NumConstraints(int k) const { return Initialized().GetProblem().NumConstraints(k); }
+  int NumConstraints() const { return Initialized().GetProblem().NumConstraints(); }
   // dual variables of knot k, equalities then inequalities (GetALCost(k)->...->GetDuals() there)
   VectorXd GetDuals(int k) {
     const std::vector<double> lam = core_->Duals(k, 0);
@@ -129,6 +129,12 @@ class AugmentedLagrangianiLQR {
   }
 
  private:
+  // a solver made with the (N) constructor has no device state until InitializeFromProblem
+  detail::DeviceSolver& Initialized() const {
+    ALTRO_ASSERT(core_ != nullptr, "Solver is empty: finish initializing the solver with a problem (InitializeFromProblem).");
+    if (!core_) throw DeviceError(ALTRO_B200_ERR_STATE, "the solver has no problem yet (InitializeFromProblem)");
+    return *core_;
+  }
   static double InfNorm(const VectorXd& v) {
     double r = 0.0;
     for (int i = 0; i < v.size(); ++i) r = std::fabs(v(i)) > r ? std::fabs(v(i)) : r;

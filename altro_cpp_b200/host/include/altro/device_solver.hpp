@@ -38,7 +38,7 @@ class DeviceSolver {
   // devices: more than one entry shards the batch over those GPUs (altro_b200_multi_*): whole solves only
   DeviceSolver(const problem::Problem& prob, int n, int m, bool use_constraints, int batch = 1, int device = 0,
                std::vector<int> devices = {})
-      : prob_(prob), n_(n), m_(m), N_(prob.NumSegments()), B_(batch), device_(device),
+      : prob_(prob.ConstrainedProblem()), n_(n), m_(m), N_(prob.NumSegments()), B_(batch), device_(device),
         use_constraints_(use_constraints), devices_(std::move(devices)) {
     if (!prob_.IsFullyDefined()) throw std::invalid_argument("Expected problem to be fully defined.");
     if (batch < 1) throw std::invalid_argument("batch must be positive");

@@ -29,3 +29,10 @@ using RowMajorNxMd = Eigen::Matrix<double, n, m, Eigen::RowMajor>;
 using RowMajorXd = RowMajorNxMd<Eigen::Dynamic, Eigen::Dynamic>;
 
 }  // namespace altro
+
+// Programs that print matrices with fmt ("{}" of a VectorXd) relied on fmt < 9 picking up operator<< by itself;
+// newer fmt wants the formatter named.  Only when the program has included fmt before this header.
+#if defined(FMT_VERSION) && FMT_VERSION >= 90000 && defined(FMT_OSTREAM_H_)
+template <class T, int R, int C, int Opt>
+struct fmt::formatter<Eigen::Matrix<T, R, C, Opt>> : fmt::ostream_formatter {};
+#endif

@@ -20,6 +20,7 @@ class DynamicsExpansion : public StateControlSized<n, m> {
       : StateControlSized<n, m>(state_dim, control_dim), jac_(MatrixXd::Zero(state_dim, state_dim + control_dim)) {}
   MatrixXd& GetJacobian() { return jac_; }
   const MatrixXd& GetJacobian() const { return jac_; }
+  void SetZero() { jac_.setZero(); }
   // writable views of the two blocks (assigning to them fills the Jacobian)
   Eigen::Ref<MatrixXd> GetA() { return jac_.topLeftCorner(this->n_, this->n_); }
   Eigen::Ref<MatrixXd> GetB() { return jac_.topRightCorner(this->n_, this->m_); }

@@ -115,17 +115,19 @@ class Problem {
     return ok;
   }
 
-  // Set by augmented_lagrangian::BuildAugLagProblem: an iLQR solver built from this problem minimises the
-  // augmented Lagrangian of its constraints (the reference wraps every cost in an ALCost object instead)
-  void MarkAugmentedLagrangian(bool v) { auglag_ = v; }
-  bool IsAugmentedLagrangian() const { return auglag_; }
+  // Set by augmented_lagrangian::BuildAugLagProblem on the problem it returns (costs wrapped in ALCost objects, no
+  // constraints of its own): `constrained` is the problem it was built from.  A solver built from the marked
+  // problem describes `constrained` to the device and asks the kernels for the augmented-Lagrangian terms.
+  void MarkAugmentedLagrangian(std::shared_ptr<const Problem> constrained) { auglag_source_ = std::move(constrained); }
+  bool IsAugmentedLagrangian() const { return auglag_source_ != nullptr; }
+  const Problem& ConstrainedProblem() const { return auglag_source_ ? *auglag_source_ : *this; }
 
  private:
   void AddConstraint(constraints::ConstraintPtr<constraints::Equality> con, int k) { eq_.at(k).emplace_back(std::move(con)); }
   void AddConstraint(constraints::ConstraintPtr<constraints::Inequality> con, int k) { ineq_.at(k).emplace_back(std::move(con)); }
 
   int N_;
-  bool auglag_ = false;
+  std::shared_ptr<const Problem> auglag_source_;
   std::shared_ptr<VectorXd> initial_state_;
   std::vector<std::shared_ptr<CostFunction>> costfuns_;
   std::vector<std::shared_ptr<DiscreteDynamics>> models_;

@@ -191,12 +191,49 @@ class Reporter {
 
 }  // namespace internal
 
-inline void InitGoogleTest(int*, char**) {}
+namespace internal {
+// --gtest_filter=POSITIVE[-NEGATIVE], each a ':'-separated list of glob patterns ('*' and '?') on "Suite.Name"
+inline std::string& Filter() {
+  static std::string filter = "*";
+  return filter;
+}
+inline bool GlobMatch(const char* pat, const char* text) {
+  if (*pat == '\0') return *text == '\0';
+  if (*pat == '*') return GlobMatch(pat + 1, text) || (*text != '\0' && GlobMatch(pat, text + 1));
+  return *text != '\0' && (*pat == '?' || *pat == *text) && GlobMatch(pat + 1, text + 1);
+}
+inline bool AnyPatternMatches(const std::string& patterns, const std::string& name) {
+  std::size_t start = 0;
+  while (start <= patterns.size()) {
+    std::size_t stop = patterns.find(':', start);
+    if (stop == std::string::npos) stop = patterns.size();
+    if (stop > start && GlobMatch(patterns.substr(start, stop - start).c_str(), name.c_str())) return true;
+    start = stop + 1;
+  }
+  return false;
+}
+inline bool Selected(const std::string& name) {
+  const std::string& f = Filter();
+  const std::size_t dash = f.find('-');
+  const std::string positive = dash == std::string::npos ? f : f.substr(0, dash);
+  const std::string negative = dash == std::string::npos ? std::string() : f.substr(dash + 1);
+  return AnyPatternMatches(positive.empty() ? std::string("*") : positive, name) && !AnyPatternMatches(negative, name);
+}
+}  // namespace internal
+
+inline void InitGoogleTest(int* argc, char** argv) {
+  const std::string flag = "--gtest_filter=";
+  for (int i = 1; argc && i < *argc; ++i) {
+    const std::string arg = argv[i];
+    if (arg.compare(0, flag.size(), flag) == 0) internal::Filter() = arg.substr(flag.size());
+  }
+}
 inline void InitGoogleTest() {}
 
 inline int RunAllTests() {
   int failed = 0, ran = 0;
   for (const internal::Entry& e : internal::Registry()) {
+    if (!internal::Selected(e.suite + "." + e.name)) continue;
     std::printf("[ RUN      ] %s.%s\n", e.suite.c_str(), e.name.c_str());
     std::fflush(stdout);
     internal::State::Get().failures_in_current = 0;

@@ -34,11 +34,27 @@ def available():
     return os.path.isdir(os.path.join(REF, "perf")) and fmt_include() is not None
 
 
+def ref_include_dir():
+    """An include root that shows the reference's examples/, perf/ and test/ trees but NOT its altro/ headers, so
+    that `#include "altro/..."` can only ever resolve to this repo's mirror (a header the mirror lacks is a
+    compile error, not a silent fall-back to the reference's implementation)."""
+    import tempfile
+    inc = os.path.join(tempfile.gettempdir(), "altro_b200_ref_include")  # links only; kept out of the snapshot
+    os.makedirs(inc, exist_ok=True)
+    for name in os.listdir(REF):
+        src, dst = os.path.join(REF, name), os.path.join(inc, name)
+        if name == "altro" or not os.path.isdir(src) or name.startswith("."):
+            continue
+        if not os.path.islink(dst):
+            os.symlink(src, dst)
+    return inc
+
+
 def build(verbose=False):
     """-> {program: path}.  Raises CalledProcessError (with the compiler output) on any failure."""
     os.makedirs(OUT, exist_ok=True)
     inc = ["-I", os.path.join(ROOT, "altro_cpp_b200", "host", "include"), "-I", os.path.join(ROOT, "include"),
-           "-I", REF, "-I", fmt_include(), "-DFMT_HEADER_ONLY", f'-DLOCAL_LOG_DIR="{OUT}"']
+           "-I", ref_include_dir(), "-I", fmt_include(), "-DFMT_HEADER_ONLY", f'-DLOCAL_LOG_DIR="{OUT}"']
     flags = ["g++", "-std=c++14", "-O1", "-DNDEBUG"]  # the reference's CI builds Release
     objs = []
     procs = []

@@ -2,12 +2,18 @@
 mirror: compiled where they lie under /root/reference with the mirror's headers, the Eigen stand-in and a small
 GoogleTest stand-in (tests/cpp/gtest_standin), linked with libaltro_b200.so (tests/ref_unit_tests.py).
 
-* host-side classes (KnotPoint, Problem, cost / dynamics functors, derivative checks, expansions, thread pool, timer,
-  logger, options): 16 test programs, run here on the CPU;
-* solver tests (unicycle_ilqr_test, ilqr_test, ilqr_class_test, example_unicycle_test, example_triple_integrator_test): built
-  here, run on the GPU box from the executables that travel with the snapshot — the reference's golden iteration
-  counts, costs, step lengths and gains, asserted by the reference's own code, on the device.
+All 25 programs of the reference's test/ tree are built:
+
+* host-side classes (KnotPoint, Problem, cost / dynamics / constraint functors, ConstraintValues, KnotPointFunctions
+  arithmetic, derivative checks, expansions, thread pool, timer, logger, options, benchmarking): 19 programs, run here
+  on the CPU, plus the cases of auglag_test that launch no kernel;
+* solver tests (unicycle_ilqr_test, ilqr_test, ilqr_class_test, example_unicycle_test, example_triple_integrator_test,
+  auglag_test): built here, run on the GPU box from the executables that travel with the snapshot — the reference's
+  golden iteration counts, costs, step lengths, gains and violations, asserted by the reference's own code, on the
+  device.  The two EXPECT_DOUBLE_EQ (4 ulp) assertions on a final cost are the only ones the device cannot meet; they
+  are checked to 1e-10 relative instead and reported (ref_unit_tests.ULP_ASSERTIONS).
 """
+import re
 import importlib.util
 import os
 import subprocess
@@ -54,6 +60,25 @@ def test_reference_host_side_unit_test_passes(built, rel):
     assert " 0 failed." in out
 
 
+@pytest.mark.parametrize("rel", sorted(ref_unit.HOST_CASES_OF_DEVICE_TESTS))
+def test_reference_solver_test_cases_that_need_no_device_pass(built, rel):
+    exe, log = built[rel]
+    assert exe is not None, log[-1500:]
+    rc, out, err = ref_unit.run_test(exe, gtest_filter=ref_unit.HOST_CASES_OF_DEVICE_TESTS[rel])
+    assert rc == 0, out[-2000:] + err[-2000:]
+    assert " 0 failed." in out and "tests ran" in out and "[==========] 0 tests" not in out
+
+
+def test_reference_builds_never_see_the_reference_headers(built):
+    """`#include "altro/..."` must resolve to the mirror: the include root handed to the compiler shows the reference's
+    examples/, perf/ and test/ trees only."""
+    inc = ref_unit._ref_include_dir()
+    assert not os.path.exists(os.path.join(inc, "altro"))
+    deps = subprocess.run(ref_unit._flags() + ["-M", os.path.join(ref_unit.REF, "test", "problem", "unicycle_test.cpp")],
+                          capture_output=True, text=True).stdout
+    assert "/root/reference/altro/" not in deps and "host/include/altro/utils/benchmarking.hpp" in deps
+
+
 def test_reference_solver_tests_are_loud_without_a_gpu(built):
     if _has_gpu():
         pytest.skip("a GPU is present")
@@ -70,6 +95,20 @@ def test_reference_solver_unit_test_passes_on_the_device(rel):
     if not os.path.exists(exe):
         pytest.skip("not built (tests/_ref_build/unit is produced where /root/reference is mounted)")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
-    tail = "\n".join(l for l in (r.stdout + r.stderr).splitlines() if "Failure" in l or "FAILED" in l or "Expected" in l or "actual" in l)[-3000:]
+    text = r.stdout + r.stderr
+    tail = "\n".join(l for l in text.splitlines() if "Failure" in l or "FAILED" in l or "Expected" in l or "actual" in l)[-3000:]
+    ulp = ref_unit.ULP_ASSERTIONS.get(rel)
+    if ulp and r.returncode != 0:
+        # every reported failure must be one of the known 4-ulp assertions, and within rel_tol of the golden value
+        where = re.findall(r"^(\S+):(\d+): Failure\n(.*)$", text, flags=re.M)
+        assert where and "unexpected exception" not in text, tail
+        assert len(where) == len(re.findall(r"^\[  FAILED  \]", r.stdout, flags=re.M)), tail  # one assertion per failed case
+        for path, line, detail in where:
+            assert path.endswith(rel) and int(line) in ulp["lines"], tail
+            got = float(re.search(r": (\S+) vs ", detail).group(1))
+            rel_err = abs(got - ulp["golden"]) / abs(ulp["golden"])
+            print(f"{rel}:{line}: EXPECT_DOUBLE_EQ not met, device {got!r} vs {ulp['golden']!r}: rel {rel_err:.2e}")
+            assert rel_err < ulp["rel_tol"], tail
+        return
     assert r.returncode == 0, tail
     assert " 0 failed." in r.stdout
