@@ -189,6 +189,57 @@ void TestDescriptors() {
   EXPECT(code == ALTRO_B200_ERR_UNSUPPORTED);
 }
 
+// The Eigen stand-in's factorisations (the reference's tests compare gains against ldlt().solve(); QuadraticCost
+// validation reads the signs of vectorD()): residuals on a matrix that needs pivoting, and on an SPD one.
+void TestStandInFactorisations() {
+  MatrixXd A(3, 3);
+  A << 1e-8, 2.0, 0.0,  //
+      2.0, 1.0, 3.0,    //
+      0.0, 3.0, -4.0;
+  MatrixXd rhs(3, 2);
+  rhs << 1.0, -2.0, 0.5, 4.0, -3.0, 0.25;
+  const auto ldlt = A.ldlt();
+  const MatrixXd x = ldlt.solve(rhs);
+  EXPECT((A * x - rhs).norm() < 1e-12);
+  int negative = 0;
+  for (int i = 0; i < 3; ++i) negative += ldlt.vectorD()(i) < 0.0;
+  EXPECT(negative == 2);  // det(A) > 0 and a negative diagonal entry: inertia (1, 2)
+
+  MatrixXd S = A.transpose() * A + MatrixXd::Identity(3, 3);
+  EXPECT((S * S.llt().solve(rhs) - rhs).norm() < 1e-10);
+  EXPECT((S * S.ldlt().solve(rhs) - rhs).norm() < 1e-10);
+  EXPECT(S.llt().info() == Eigen::Success && A.llt().info() != Eigen::Success);
+}
+
+// The AL terms of one knot evaluated on the host (ALCost built from a problem, not from a solver) against the
+// closed form for a goal constraint: J = l(x,u) + lambda'(x - xf)... with the sign convention of the reference,
+// (|lambda - rho c|^2 - |lambda|^2) / (2 rho).
+void TestStandaloneALCost() {
+  UnicycleProblem def;
+  altro::problem::Problem prob = def.MakeProblem();
+  const int N = prob.NumSegments();
+  altro::augmented_lagrangian::ALCost<3, 2> term(prob, N);
+  EXPECT(term.NumConstraints() == 3 && term.GetEqualityConstraints().size() == 1);
+  const double rho = 7.0;
+  term.SetPenalty<altro::constraints::Equality>(rho);
+  VectorXd& lambda = term.GetEqualityConstraints()[0]->GetDuals();
+  lambda << 0.3, -0.2, 0.1;
+  VectorXd x(3), u(2);
+  x << 0.4, 1.2, 0.9;
+  u << 0.0, 0.0;
+  VectorXd c(3);
+  prob.GetEqualityConstraints()[N][0]->Evaluate(x, u, c);
+  double expected = prob.GetCostFunction(N)->Evaluate(x, u);
+  for (int i = 0; i < 3; ++i) expected += (std::pow(lambda(i) - rho * c(i), 2) - lambda(i) * lambda(i)) / (2 * rho);
+  EXPECT(std::fabs(term.Evaluate(x, u) - expected) < 1e-12);
+  // the problem BuildAugLagProblem returns evaluates the same terms and has no constraints of its own
+  altro::problem::Problem prob_al = altro::augmented_lagrangian::BuildAugLagProblem<3, 2>(prob);
+  EXPECT(prob_al.NumConstraints() == 0 && prob.NumConstraints() > 0 && prob_al.IsAugmentedLagrangian());
+  double unit = prob.GetCostFunction(N)->Evaluate(x, u);
+  for (int i = 0; i < 3; ++i) unit += 0.5 * c(i) * c(i);  // multipliers zero, penalty one
+  EXPECT(std::fabs(prob_al.GetCostFunction(N)->Evaluate(x, u) - unit) < 1e-12);
+}
+
 // without a GPU every solver reports the CUDA error instead of computing on the host
 void TestNoDeviceIsLoud() {
   UnicycleProblem def;
@@ -443,6 +494,8 @@ int main(int argc, char* argv[]) {
   const bool gpu = argc > 1 && std::strcmp(argv[1], "gpu") == 0;
   try {
     TestDescriptors();
+    TestStandInFactorisations();
+    TestStandaloneALCost();
     if (!gpu) {
       TestNoDeviceIsLoud();
     } else {
