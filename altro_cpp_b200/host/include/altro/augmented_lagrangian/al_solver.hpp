@@ -49,7 +49,10 @@ class AugmentedLagrangianiLQR {
   ilqr::iLQR<n, m>& GetiLQRSolver() { return ilqr_solver_; }
   SolverOptions& GetOptions() { return Initialized().GetOptions(); }
   SolverStats& GetStats() { return Initialized().GetStats(); }
-  SolverStatus GetStatus() { return static_cast<SolverStatus>(Initialized().Pull().status[0]); }
+  // the device's verdict after Solve(); the verdict of IsDone() when the caller runs the outer loop step by step
+  SolverStatus GetStatus() {
+    return by_hand_ ? status_by_hand_ : static_cast<SolverStatus>(Initialized().Pull().status[0]);
+  }
   int NumSegments() const { return ilqr_solver_.NumSegments(); }
 
   void SetPenalty(double rho) { core_->SetPenalty(rho); }
@@ -59,6 +62,7 @@ class AugmentedLagrangianiLQR {
     auto Z = ilqr_solver_.GetTrajectory();
     ALTRO_ASSERT(Z != nullptr, "Invalid trajectory pointer. May be uninitialized.");
     if (!Z) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
+    by_hand_ = false;
     core_->Upload(*Z);
     core_->Run(detail::DeviceSolver::kSolveAL);
     core_->Download(Z.get());
@@ -70,14 +74,50 @@ class AugmentedLagrangianiLQR {
   void Init() {
     auto Z = ilqr_solver_.GetTrajectory();
     if (!Z) throw DeviceError(ALTRO_B200_ERR_STATE, "Invalid trajectory pointer. May be uninitialized.");
+    by_hand_ = false;
     core_->Upload(*Z);
     core_->Run(detail::DeviceSolver::kAlInit);
-    GetStats().Reset();
+    SolverStats& stats = GetStats();
+    stats.Reset();
+    stats.Log("iter_al", 0);
+    stats.Log("viol", MaxViolation());
+    stats.Log("pen", GetMaxPenalty());
   }
+  // ---- the outer loop step by step (what Solve() runs in one launch; al_solver.hpp:304-334 there):
+  //   Init(); loop { GetiLQRSolver().Solve(); UpdateDuals(); UpdateConvergenceStatistics(); if (IsDone()) break;
+  //                  UpdatePenalties(); }
   void UpdateDuals() { core_->Run(detail::DeviceSolver::kUpdateDuals); }
   void UpdatePenalties() { core_->Run(detail::DeviceSolver::kUpdatePenalties); }
+  void ResetDualVariables() { Initialized().ZeroDuals(); }
+  void UpdateConvergenceStatistics() {
+    Initialized().CountOuterIterationByHand();
+    const double viol = GetMaxViolation();  // pulls the counters: iterations_outer now includes this iteration
+    SolverStats& stats = GetStats();
+    stats.Log("viol", viol);
+    stats.Log("pen", GetMaxPenalty());
+    stats.Log("iter_al", stats.iterations_outer);
+  }
+  // the termination tests of al_solver.hpp:368-400 there, on the statistics logged last
+  bool IsDone() {
+    SolverStats& stats = GetStats();
+    const SolverOptions& opts = GetOptions();
+    const SolverStatus inner = ilqr_solver_.GetStatus();
+    by_hand_ = true;
+    if (inner != SolverStatus::kSolved) return Verdict(inner);
+    if (!stats.violations.empty() && stats.violations.back() < opts.constraint_tolerance) return Verdict(SolverStatus::kSolved);
+    if (!stats.max_penalty.empty() && stats.max_penalty.back() > opts.maximum_penalty) return Verdict(SolverStatus::kMaxPenalty);
+    if (stats.iterations_outer >= opts.max_iterations_outer) return Verdict(SolverStatus::kMaxOuterIterations);
+    if (stats.iterations_total >= opts.max_iterations_total) return Verdict(SolverStatus::kMaxIterations);
+    status_by_hand_ = SolverStatus::kUnsolved;
+    return false;
+  }
   double MaxViolation() {
     core_->Run(detail::DeviceSolver::kCost);
+    return core_->Pull().viol[0];
+  }
+  // of another trajectory: it becomes the solver's current iterate on the device, as ilqr.Cost(Z) does there
+  double MaxViolation(const Trajectory<n, m>& Z) {
+    ilqr_solver_.Cost(Z);
     return core_->Pull().viol[0];
   }
   double GetMaxViolation() { return MaxViolation(); }
@@ -135,12 +175,18 @@ class AugmentedLagrangianiLQR {
     if (!core_) throw DeviceError(ALTRO_B200_ERR_STATE, "the solver has no problem yet (InitializeFromProblem)");
     return *core_;
   }
+  bool Verdict(SolverStatus status) {
+    status_by_hand_ = status;
+    return true;
+  }
   static double InfNorm(const VectorXd& v) {
     double r = 0.0;
     for (int i = 0; i < v.size(); ++i) r = std::fabs(v(i)) > r ? std::fabs(v(i)) : r;
     return r;
   }
   int device_ = 0;
+  bool by_hand_ = false;  // the last verdict came from IsDone(), not from a whole-solve launch
+  SolverStatus status_by_hand_ = SolverStatus::kUnsolved;
   std::shared_ptr<detail::DeviceSolver> core_;
   ilqr::iLQR<n, m> ilqr_solver_;
   std::vector<std::shared_ptr<ALCost<n, m>>> costs_;

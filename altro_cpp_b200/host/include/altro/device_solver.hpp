@@ -171,6 +171,20 @@ class DeviceSolver {
   void PushDualsBeforeNextRun(int k, int row0, std::shared_ptr<VectorXd> values) {
     pending_duals_.push_back({k, row0, std::move(values)});
   }
+  // An outer (dual-update) iteration the caller performed step by step (AugmentedLagrangianiLQR::
+  // UpdateConvergenceStatistics): the device counts only the outer iterations of whole solves.
+  void CountOuterIterationByHand() { ++outer_by_hand_; }
+  // all multipliers of every instance to zero (AugmentedLagrangianiLQR::ResetDualVariables)
+  void ZeroDuals() {
+    Need();
+    pending_duals_.clear();
+    for (int k = 0; k <= N_; ++k) {
+      const int rows = prob_.NumConstraints(k);
+      if (rows == 0) continue;
+      const std::vector<double> zeros(static_cast<size_t>(rows), 0.0);
+      Check(altro_b200_solver_set_duals_host(solver_, k, zeros.data(), rows, nullptr), "ResetDualVariables");
+    }
+  }
   void FlushPendingDuals() {
     if (pending_duals_.empty() || Sharded() || !solver_) return;
     std::vector<PendingDuals> todo;
@@ -200,6 +214,7 @@ class DeviceSolver {
     }
     Need();
     PushOptions();
+    if (ph == kSolveAL || ph == kAlInit) outer_by_hand_ = 0;  // the device counts the outer iterations of a whole solve
     int rc = ALTRO_B200_ERR_ARG;
     switch (ph) {
       case kRollout: rc = altro_b200_rollout(solver_, nullptr); break;
@@ -242,7 +257,7 @@ class DeviceSolver {
                                       nullptr, res_.initial_cost.data(), nullptr),
           "GetStats");
     stats_.iterations_inner = res_.iters[0];
-    stats_.iterations_outer = res_.iters[1];
+    stats_.iterations_outer = res_.iters[1] + outer_by_hand_;
     stats_.iterations_total = res_.iters[2];
     stats_.initial_cost = res_.initial_cost[0];
     return res_;
@@ -513,6 +528,7 @@ class DeviceSolver {
   altro_b200_multi* multi_ = nullptr;
   std::vector<float> t_, h_all_;
   bool have_step_ = false;
+  int outer_by_hand_ = 0;
   double penalty_ = 0.0;
   bool have_penalty_ = false;
   double penalty_scaling_ = 0.0;

@@ -5,6 +5,7 @@
 //
 //   host_mirror_test cpu   checks that need no GPU (descriptor plumbing, loud failure)
 //   host_mirror_test gpu   everything
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -397,6 +398,52 @@ void TestUnicycleAugLag() {
   }
 }
 
+// The outer loop driven by the caller with the reference's public step methods (al_solver.hpp:304-334 there) must
+// walk the same path as Solve(), which runs it in one launch: same verdict, iteration counts, cost and trajectory.
+void TestOuterLoopByHand() {
+  UnicycleProblem def;
+  auto whole = def.MakeALSolver();
+  whole.GetOptions().constraint_tolerance = 1e-6;
+  *whole.GetiLQRSolver().GetTrajectory() = def.InitialTrajectory();
+  whole.Solve();
+  const double J_whole = whole.GetiLQRSolver().Cost();
+
+  auto steps = def.MakeALSolver();
+  steps.GetOptions().constraint_tolerance = 1e-6;
+  *steps.GetiLQRSolver().GetTrajectory() = def.InitialTrajectory();
+  steps.Init();
+  EXPECT(steps.GetStats().iterations_outer == 0 && steps.GetStats().violations.size() == 1);
+  EXPECT(steps.GetStatus() == SolverStatus::kUnsolved);
+  int passes = 0;
+  for (; passes < steps.GetOptions().max_iterations_outer; ++passes) {
+    steps.GetiLQRSolver().Solve();
+    steps.UpdateDuals();
+    steps.UpdateConvergenceStatistics();
+    if (steps.IsDone()) break;
+    steps.UpdatePenalties();
+  }
+  EXPECT(steps.GetStatus() == whole.GetStatus() && steps.GetStatus() == SolverStatus::kSolved);
+  EXPECT(passes + 1 == whole.GetStats().iterations_outer);
+  EXPECT(steps.GetStats().iterations_outer == whole.GetStats().iterations_outer);
+  EXPECT(steps.GetStats().iterations_total == whole.GetStats().iterations_total);
+  EXPECT(steps.GetMaxPenalty() == whole.GetMaxPenalty());
+  const double J_steps = steps.GetiLQRSolver().Cost();
+  EXPECT(J_steps == J_whole);
+  if (J_steps != J_whole) std::printf("  by hand %.17g, whole solve %.17g\n", J_steps, J_whole);
+  const auto Za = whole.GetiLQRSolver().GetTrajectory(), Zb = steps.GetiLQRSolver().GetTrajectory();
+  double worst = 0.0;
+  for (int k = 0; k <= def.N; ++k) worst = std::max(worst, (Za->State(k) - Zb->State(k)).norm());
+  EXPECT(worst == 0.0);
+
+  // ResetDualVariables: every multiplier back to zero, the penalty untouched
+  const double pen = steps.GetMaxPenalty();
+  steps.ResetDualVariables();
+  EXPECT(steps.GetDuals(def.N).norm() == 0.0 && steps.GetDuals(1).norm() == 0.0);
+  EXPECT(steps.GetMaxPenalty() == pen);
+  // MaxViolation(Z) of another trajectory: the initial guess violates the goal constraint
+  EXPECT(steps.MaxViolation(def.InitialTrajectory()) > 1e-2);
+}
+
 // test/examples/example_unicycle_test.cpp:69-89 (BASELINE config C1)
 void TestThreeObstacles() {
   UnicycleProblem def;
@@ -501,6 +548,7 @@ int main(int argc, char* argv[]) {
     } else {
       TestUnicycleILQR();
       TestUnicycleAugLag();
+      TestOuterLoopByHand();
       TestNonUniformSteps();
       TestThreeObstacles();
       TestTripleIntegrator();
