@@ -191,6 +191,10 @@ class BatchSolver:
     def set_penalty(self, rho: float, stream=None):
         self._call("solver_set_penalty", ctypes.c_double(rho), _stream_ptr(stream))
 
+    def set_initial_cost(self, cost: float, stream=None):
+        """stats.initial_cost of every instance (step-wise iterations; a whole solve sets it itself)."""
+        self._call("solver_set_initial_cost", ctypes.c_double(cost), _stream_ptr(stream))
+
     def set_duals(self, k: int, lam, stream=None):
         lam = _f64(lam)
         self._call("solver_set_duals_host", ctypes.c_int(k), _p(lam), ctypes.c_int(lam.size), _stream_ptr(stream))
@@ -256,6 +260,12 @@ class BatchSolver:
         P = np.zeros((self.B, self.n, self.n)); p = np.zeros((self.B, self.n))
         self._call("get_ctg_host", ctypes.c_int(k), _p(P), _p(p), _stream_ptr(stream))
         return np.ascontiguousarray(P.transpose(0, 2, 1)), p
+
+    def costs(self, stream=None):
+        """per-knot costs [B,N+1] of the last cost() / update_expansions() (the reference's GetCosts())."""
+        c = np.zeros((self.B, self.N + 1))
+        self._call("get_costs_host", _p(c), _stream_ptr(stream))
+        return c
 
     def expansion(self, k, stream=None):
         n, m, B = self.n, self.m, self.B

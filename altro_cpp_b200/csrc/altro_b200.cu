@@ -1184,6 +1184,11 @@ int altro_b200_solver_set_penalty(altro_b200_solver* s, double rho, void* stream
   DeviceGuard guard(s->device);
   return fill_scalar(s, S_PENALTY, rho, S(stream));
 }
+int altro_b200_solver_set_initial_cost(altro_b200_solver* s, double cost, void* stream) {
+  if (!s || cost != cost) return fail(ALTRO_B200_ERR_ARG, "set_initial_cost: bad argument");
+  DeviceGuard guard(s->device);
+  return fill_scalar(s, S_INITIAL_COST, cost, S(stream));
+}
 int altro_b200_solver_set_duals_host(altro_b200_solver* s, int k, const double* lambda, int p, void* stream) {
   if (!s || !lambda || k < 0 || k > s->N || p < 0 || p > s->pmax)
     return fail(ALTRO_B200_ERR_ARG, "set_duals: bad argument");
@@ -1603,6 +1608,12 @@ int altro_b200_get_ctg_host(altro_b200_solver* s, int k, double* Pm, double* p, 
   if (Pm && (rc = unpack_to(s, s->P.CTG, s->N + 1, F, 0, s->n * s->n, k, 1, Pm, true, false, S(stream)))) return rc;
   if (p && (rc = unpack_to(s, s->P.CTG, s->N + 1, F, s->n * s->n, s->n, k, 1, p, true, false, S(stream)))) return rc;
   return 0;
+}
+int altro_b200_get_costs_host(altro_b200_solver* s, double* costs, void* stream) {
+  if (!s || !costs) return fail(ALTRO_B200_ERR_ARG, "get_costs: bad argument");
+  if (!s->P.COSTS) return fail(ALTRO_B200_ERR_STATE, "Cost / UpdateExpansions has not run");
+  DeviceGuard guard(s->device);
+  return unpack_to(s, s->P.COSTS, s->N + 1, 1, 0, 1, 0, s->N + 1, costs, true, false, S(stream));
 }
 int altro_b200_get_expansion_host(altro_b200_solver* s, int k, double* A, double* Bm, double* lxx, double* lxu,
                                   double* luu, double* lx, double* lu, void* stream) {

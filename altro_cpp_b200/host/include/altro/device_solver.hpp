@@ -215,6 +215,7 @@ class DeviceSolver {
     Need();
     PushOptions();
     if (ph == kSolveAL || ph == kAlInit) outer_by_hand_ = 0;  // the device counts the outer iterations of a whole solve
+    if (ph == kSolveAL || ph == kSolveILQR) take_initial_cost_ = true;  // a whole solve measures it itself
     int rc = ALTRO_B200_ERR_ARG;
     switch (ph) {
       case kRollout: rc = altro_b200_rollout(solver_, nullptr); break;
@@ -259,7 +260,8 @@ class DeviceSolver {
     stats_.iterations_inner = res_.iters[0];
     stats_.iterations_outer = res_.iters[1] + outer_by_hand_;
     stats_.iterations_total = res_.iters[2];
-    stats_.initial_cost = res_.initial_cost[0];
+    if (take_initial_cost_) stats_.initial_cost = res_.initial_cost[0];  // else the caller's (step-wise iterations)
+    take_initial_cost_ = false;
     return res_;
   }
   const Results& Last() const { return res_; }
@@ -281,6 +283,19 @@ class DeviceSolver {
     for (int j = 0; j < n_; ++j)
       for (int i = 0; i < n_; ++i) (*P)(i, j) = Pall[static_cast<size_t>(b) * n_ * n_ + j * n_ + i];
     for (int i = 0; i < n_; ++i) (*p)(i) = pall[static_cast<size_t>(b) * n_ + i];
+  }
+  // costs_(k), k = 0 .. N, of instance b as the last Cost() / UpdateExpansions() left them
+  std::vector<double> Costs(int b) {
+    Need();
+    std::vector<double> all(static_cast<size_t>(B_) * (N_ + 1));
+    Check(altro_b200_get_costs_host(solver_, all.data(), nullptr), "GetCosts");
+    return std::vector<double>(all.begin() + static_cast<size_t>(b) * (N_ + 1),
+                               all.begin() + static_cast<size_t>(b + 1) * (N_ + 1));
+  }
+  // stats.initial_cost of a caller who runs the inner iterations one by one (ilqr.hpp:292 there)
+  void SetInitialCost(double J) {
+    Need();
+    Check(altro_b200_solver_set_initial_cost(solver_, J, nullptr), "GetStats");
   }
   // c(x_k, u_k) of instance b at knot k, ALCost row order (equalities, then inequalities)
   std::vector<double> ConstraintValues(int k, int b) {
@@ -529,6 +544,7 @@ class DeviceSolver {
   std::vector<float> t_, h_all_;
   bool have_step_ = false;
   int outer_by_hand_ = 0;
+  bool take_initial_cost_ = false;
   double penalty_ = 0.0;
   bool have_penalty_ = false;
   double penalty_scaling_ = 0.0;

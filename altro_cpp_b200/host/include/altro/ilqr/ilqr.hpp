@@ -15,6 +15,8 @@
 // rollout starts and overwritten with the device result when one ends.
 #pragma once
 
+#include <algorithm>
+#include <cmath>
 #include <functional>
 #include <memory>
 #include <utility>
@@ -67,7 +69,17 @@ class iLQR {
   int NumSegments() const { return N_; }
   SolverStats& GetStats() { return Core().GetStats(); }
   SolverOptions& GetOptions() { return Core().GetOptions(); }
-  SolverStatus GetStatus() { return static_cast<SolverStatus>(Core().Pull().ilqr_status[0]); }
+  // the device's verdict after Solve(); the verdict of IsDone() when the caller runs the iterations one by one
+  SolverStatus GetStatus() {
+    return by_hand_ ? status_by_hand_ : static_cast<SolverStatus>(Core().Pull().ilqr_status[0]);
+  }
+  // costs_(k) of the last Cost() / UpdateExpansions(), augmented-Lagrangian terms included (ilqr.hpp:163 there)
+  VectorXd& GetCosts() {
+    const std::vector<double> c = Core().Costs(0);
+    costs_ = VectorXd::Zero(static_cast<int>(c.size()));
+    for (int k = 0; k < costs_.size(); ++k) costs_(k) = c[static_cast<size_t>(k)];
+    return costs_;
+  }
   // the problem's initial state is shared, not copied (test/ilqr/ilqr_class_test.cpp:84-96 there)
   std::shared_ptr<VectorXd> GetInitialState() { return Core().GetProblem().GetInitialStatePointer(); }
   double GetRegularization() { return Core().Pull().reg[0]; }
@@ -110,6 +122,7 @@ class iLQR {
 
   void Solve() {
     Require();
+    by_hand_ = false;
     Core().Upload(*Z_);
     Core().Run(detail::DeviceSolver::kSolveILQR);
     Core().Download(Z_.get());
@@ -159,7 +172,11 @@ class iLQR {
     GetStats().Log("alpha", sc.alpha);
     GetStats().Log("z", sc.z);
   }
+  // The first iteration's decrease is measured against stats.initial_cost, which the caller of the step-wise
+  // methods assigns (`GetStats().initial_cost = Cost()`, as Solve() does there, ilqr.hpp:292): it goes to the device.
   void UpdateConvergenceStatistics() {
+    Core().Pull();
+    if (GetStats().iterations_inner == 0) Core().SetInitialCost(GetStats().initial_cost);
     Core().Run(detail::DeviceSolver::kUpdateConvergenceStatistics);
     Core().Pull();
     const auto sc = Core().Scalars();  // ilqr.hpp:578-584
@@ -169,7 +186,39 @@ class iLQR {
   }
   void SolveSetup() {
     SyncThreadBookkeeping();
+    by_hand_ = false;
     Core().Run(detail::DeviceSolver::kSolveSetup);
+    Core().Pull();
+  }
+  // ilqr.hpp:597-619 there, on the statistics of the last UpdateConvergenceStatistics()
+  bool IsDone() {
+    Core().Pull();
+    const SolverStats& stats = GetStats();
+    const SolverOptions& opts = GetOptions();
+    const auto sc = Core().Scalars();
+    const SolverStatus device = static_cast<SolverStatus>(Core().Last().ilqr_status[0]);
+    by_hand_ = true;
+    status_by_hand_ = device;
+    if (sc.dJ < opts.cost_tolerance && sc.grad < opts.gradient_tolerance) status_by_hand_ = SolverStatus::kSolved;
+    else if (stats.iterations_inner >= opts.max_iterations_inner) status_by_hand_ = SolverStatus::kMaxInnerIterations;
+    else if (stats.iterations_total >= opts.max_iterations_total) status_by_hand_ = SolverStatus::kMaxIterations;
+    return status_by_hand_ != SolverStatus::kUnsolved;
+  }
+  void WrapUp() {}
+  // mean over the knot points of max_i |d_i| / (|u_i| + 1), from the device's gains and the current controls
+  double NormalizedFeedforwardGain() {
+    Require();
+    std::vector<double> K, d;
+    Core().Gains(0, &K, &d);
+    const int mm = Core().m();
+    double sum = 0.0;
+    for (int k = 0; k < N_; ++k) {
+      double worst = 0.0;
+      for (int i = 0; i < mm; ++i)
+        worst = std::max(worst, std::fabs(d[static_cast<size_t>(k) * mm + i]) / (std::fabs(Z_->Control(k)(i)) + 1));
+      sum += worst;
+    }
+    return sum / N_;
   }
   std::shared_ptr<detail::DeviceSolver> CorePtr() const { return core_; }
 
@@ -242,6 +291,9 @@ class iLQR {
   std::shared_ptr<Trajectory<n, m>> Z_;
   std::vector<std::unique_ptr<KnotPointFunctions<n, m>>> knotpoints_;
   std::vector<char> handed_out_;  // knot points whose KnotPointFunctions reference was given to the caller
+  VectorXd costs_;
+  bool by_hand_ = false;  // the last verdict came from IsDone(), not from a whole-solve launch
+  SolverStatus status_by_hand_ = SolverStatus::kUnsolved;
   std::vector<int> work_inds_ = {0, 1};
   bool custom_work_assignment_ = false;
   int nthreads_launched_ = 0;

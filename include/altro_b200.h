@@ -187,6 +187,9 @@ int altro_b200_solver_set_inputs_dev(altro_b200_solver* s, const double* x0_dev,
 int altro_b200_solver_set_states_host(altro_b200_solver* s, const double* X, void* stream);
 /* SetPenalty(rho), al_solver.hpp:271-276 */
 int altro_b200_solver_set_penalty(altro_b200_solver* s, double rho, void* stream);
+/* stats.initial_cost = Cost() (ilqr.hpp:292 there): the cost the first inner iteration's decrease is measured
+ * against.  A whole solve sets it itself; a caller who runs the iterations step by step sets it here. */
+int altro_b200_solver_set_initial_cost(altro_b200_solver* s, double cost, void* stream);
 /* GetALCost(k)->Get{Equality,Inequality}Constraints()[i]->GetDuals() = lambda, rows in
  * ALCost order (equalities then inequalities, al_cost.hpp:264-273); same duals for every instance */
 int altro_b200_solver_set_duals_host(altro_b200_solver* s, int k, const double* lambda, int p,
@@ -255,6 +258,9 @@ int altro_b200_get_gains_host(altro_b200_solver* s, double* K, double* d, void* 
 /* GetCostToGoHessian/Gradient of knot k (knot_point_function_type.hpp:254-255), valid after
  * altro_b200_backward_pass -> P [B][n*n], p [B][n] */
 int altro_b200_get_ctg_host(altro_b200_solver* s, int k, double* P, double* p, void* stream);
+/* GetCosts() (ilqr.hpp:163 there): costs[B][N+1], the per-knot costs written by the last Cost() or
+ * UpdateExpansions() of the step-wise API (augmented-Lagrangian terms included) */
+int altro_b200_get_costs_host(altro_b200_solver* s, double* costs, void* stream);
 /* GetCostExpansion()/GetDynamicsExpansion() of knot k (knot_point_function_type.hpp:249-252),
  * valid after altro_b200_update_expansions. Each [B][...] col-major: A n*n, Bm n*m, lxx n*n,
  * lxu n*m, luu m*m, lx n, lu m */

@@ -398,6 +398,51 @@ void TestUnicycleAugLag() {
   }
 }
 
+// iLQR::Solve() spelled out with the public step methods (ilqr.hpp:284-316 there) walks the same path as the
+// one-launch Solve(): verdict, iteration count, cost, trajectory; GetCosts() adds up to Cost().
+void TestInnerLoopByHand() {
+  UnicycleProblem def;
+  auto whole = def.MakeSolver();
+  whole.Solve();
+  const double J_whole = whole.Cost();
+
+  auto steps = def.MakeSolver();
+  steps.SolveSetup();
+  steps.Rollout();
+  steps.GetStats().initial_cost = steps.Cost();
+  EXPECT(std::fabs(steps.GetStats().initial_cost - 259.27636137767087) < 1e-5);
+  int iterations = 0;
+  for (; iterations < steps.GetOptions().max_iterations_inner; ++iterations) {
+    steps.UpdateExpansions();
+    steps.BackwardPass();
+    steps.ForwardPass();
+    steps.UpdateConvergenceStatistics();
+    if (iterations == 0) {  // the first decrease is measured against the initial cost the caller assigned
+      const altro::SolverStats& st = steps.GetStats();
+      EXPECT(std::fabs(st.cost_decrease[0] - (st.initial_cost - steps.Cost())) < 1e-9 * st.initial_cost);
+      const double grad = steps.NormalizedFeedforwardGain();
+      EXPECT(std::fabs(grad - st.gradient[0]) < 1e-12 * (1.0 + grad));
+    }
+    if (steps.IsDone()) break;
+  }
+  steps.WrapUp();
+  EXPECT(steps.GetStatus() == SolverStatus::kSolved && whole.GetStatus() == SolverStatus::kSolved);
+  EXPECT(steps.GetStats().iterations_inner == whole.GetStats().iterations_inner);
+  EXPECT(iterations + 1 == whole.GetStats().iterations_inner);
+  const double J_steps = steps.Cost();
+  EXPECT(J_steps == J_whole);
+  if (J_steps != J_whole) std::printf("  by hand %.17g, whole solve %.17g\n", J_steps, J_whole);
+  double worst = 0.0;
+  for (int k = 0; k <= def.N; ++k)
+    worst = std::max(worst, (whole.GetTrajectory()->State(k) - steps.GetTrajectory()->State(k)).norm());
+  EXPECT(worst == 0.0);
+  const VectorXd& costs = steps.GetCosts();
+  EXPECT(costs.size() == def.N + 1);
+  double sum = 0.0;
+  for (int k = 0; k <= def.N; ++k) sum += costs(k);
+  EXPECT(sum == J_steps);
+}
+
 // The outer loop driven by the caller with the reference's public step methods (al_solver.hpp:304-334 there) must
 // walk the same path as Solve(), which runs it in one launch: same verdict, iteration counts, cost and trajectory.
 void TestOuterLoopByHand() {
@@ -547,6 +592,7 @@ int main(int argc, char* argv[]) {
       TestNoDeviceIsLoud();
     } else {
       TestUnicycleILQR();
+      TestInnerLoopByHand();
       TestUnicycleAugLag();
       TestOuterLoopByHand();
       TestNonUniformSteps();

@@ -817,3 +817,42 @@ def test_long_line_search_uses_looping_kernels(gpu, oracle):
     o.max_iterations_inner = 30
     errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0, options=o, max_mismatch_frac=0.0)
     assert errs["X"] <= 1e-8
+
+
+def test_costs_vector_and_caller_supplied_initial_cost(gpu, oracle):
+    """GetCosts() (ilqr.hpp:163: costs_(k) as Cost() / UpdateExpansions() leave them, AL terms included) adds up to
+    Cost() in knot order, matches the oracle knot by knot, and the first step-wise iteration measures its decrease
+    against the initial cost the caller supplies (`stats.initial_cost = Cost()`, ilqr.hpp:292, :573-574)."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    B = 37  # ragged: 4 full tiles of 8 and one of 5
+    X0 = P.perturbed_initial_states(spec, B, P.UNICYCLE_X0_SCALE)
+    s = gpu.BatchSolver(spec, B)
+    s.set_inputs(X0)
+    s.set_penalty(10.0)
+    s.solve_setup(); s.rollout()
+    J = s.cost()
+    c = s.costs()
+    assert c.shape == (B, spec.N + 1)
+    acc = np.zeros(B)
+    for k in range(spec.N + 1):
+        acc += c[:, k]
+    assert np.array_equal(acc, J)
+    for b in (0, 36):
+        r = oracle_stepper(oracle, spec, X0[b], True)
+        r.set_penalty(10.0)
+        r.rollout()
+        assert close(J[b], r.cost(), 1e-12)
+    s.update_expansions()
+    assert np.array_equal(s.costs(), c)  # UpdateExpansions() rewrites the same numbers (Q7)
+    s.set_initial_cost(1234.5)
+    s.backward_pass(); s.forward_pass(); s.update_convergence_statistics()
+    sc = s.scalars()
+    assert np.all(sc["initial_cost"] == 1234.5)
+    Jn = s.cost()
+    took_a_step = Jn < J  # an instance whose line search failed keeps its iterate and logs no new cost
+    assert took_a_step.mean() > 0.9
+    assert np.allclose(sc["dJ"][took_a_step], 1234.5 - Jn[took_a_step], rtol=1e-12, atol=0)
+    # a whole solve measures its own
+    s.set_inputs(X0)
+    s.solve_al()
+    assert np.all(s.scalars()["initial_cost"] != 1234.5)
