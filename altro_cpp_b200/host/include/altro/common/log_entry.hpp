@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <type_traits>
 #include <utility>
 
 namespace altro {
@@ -24,6 +25,8 @@ class LogEntry {
   LogEntry& SetWidth(int width) { width_ = width; return *this; }
   LogEntry& SetLevel(LogLevel level) { level_ = level; return *this; }
   LogEntry& SetType(EntryType type) { type_ = type; return *this; }
+  LogEntry& SetName(const std::string& name) { name_ = name; return *this; }  // key in the logger; the title is what prints
+  const std::string& GetName() const { return name_.empty() ? title_ : name_; }
   template <class Color>
   LogEntry& SetLowerBound(double bound, Color) { lower_ = bound; has_lower_ = true; return *this; }
   LogEntry& SetLowerBound(double bound) { lower_ = bound; has_lower_ = true; return *this; }
@@ -50,6 +53,20 @@ class LogEntry {
     text_ = value;
   }
   void Clear() { text_.clear(); has_value_ = false; }
+  // one cell / one header cell on stdout, when the column is shown at `level`
+  void Print(LogLevel level = LogLevel::kSilent) const {
+    if (IsActive(level)) std::fputs(Cell().c_str(), stdout);
+  }
+  template <class Color>
+  void PrintHeader(LogLevel level, Color) const { PrintHeader(level); }
+  void PrintHeader(LogLevel level = LogLevel::kSilent) const {
+    if (IsActive(level)) std::fputs(HeaderCell().c_str(), stdout);
+  }
+  template <class T, class = typename std::enable_if<!std::is_same<T, LogLevel>::value>::type>
+  void Print(T value) {
+    Log(value);
+    Print();
+  }
   // the cell, right-aligned in the column
   std::string Cell() const { return Pad(text_); }
   std::string HeaderCell() const { return Pad(title_); }
@@ -79,7 +96,7 @@ class LogEntry {
     }
     return buf;
   }
-  std::string title_, format_ = "{}", text_;
+  std::string title_, name_, format_ = "{}", text_;
   EntryType type_ = kFloat;
   LogLevel level_ = LogLevel::kInner;
   int width_ = 10;

@@ -39,9 +39,21 @@ class SolverLogger {
   }
   LogEntry* Find(const std::string& title) {
     for (LogEntry& e : entries_)
-      if (e.GetTitle() == title) return &e;
+      if (e.GetTitle() == title || e.GetName() == title) return &e;
     return nullptr;
   }
+  // the column of that title; asking for one that does not exist appends an empty column of that title (the
+  // reference keeps its columns in a map and operator[] does the same)
+  LogEntry& GetEntry(const std::string& title) {
+    LogEntry* e = Find(title);
+    return e != nullptr ? *e : AddEntry(-1, title);
+  }
+  using iterator = std::vector<LogEntry>::iterator;
+  using const_iterator = std::vector<LogEntry>::const_iterator;
+  iterator begin() { return entries_.begin(); }
+  iterator end() { return entries_.end(); }
+  const_iterator begin() const { return entries_.begin(); }
+  const_iterator end() const { return entries_.end(); }
   // data logged to a column that is not shown at the current level (or does not exist) is discarded
   template <class T>
   void Log(const std::string& title, T value) {
@@ -56,14 +68,19 @@ class SolverLogger {
     std::fprintf(out_, "%s\n%s\n", line.c_str(), std::string(line.size(), '-').c_str());
     rows_since_header_ = 0;
   }
-  void Print() {
+  // the current row without the header logic
+  void PrintData() {
     if (level_ == LogLevel::kSilent) return;
-    if (rows_since_header_ < 0 || rows_since_header_ >= frequency_) PrintHeader();
     std::string line;
     for (const LogEntry& e : entries_)
       if (e.IsActive(level_)) line += e.Cell() + " ";
     std::fprintf(out_, "%s\n", line.c_str());
     ++rows_since_header_;
+  }
+  void Print() {
+    if (level_ == LogLevel::kSilent) return;
+    if (rows_since_header_ < 0 || rows_since_header_ >= frequency_) PrintHeader();
+    PrintData();
   }
   void Clear() {
     for (LogEntry& e : entries_) e.Clear();
