@@ -8,9 +8,12 @@
 // anything in oracle/.  The product path (altro_cpp_b200/) never includes this.
 //
 // Parity status: PINNED against the reference's own known-answer tests
-// (tests/test_oracle_golden.py lists every value with its reference file:line).
-// The reference itself cannot be compiled here (Eigen 3.3 is absent from the
-// image), so there is no oracle/_ref.
+// (tests/test_oracle_golden.py lists every value with its reference file:line)
+// and against the reference's own solver code: oracle/build_ref.py compiles it
+// where it lies on the host mirror's Eigen stand-in (Eigen 3.3 itself is absent
+// from the image) into oracle/_ref, and
+// tests/test_oracle_vs_reference_build.py finds this restatement bit-identical
+// to it on every instance it solves.
 //
 // Every function cites the reference file:line it follows.  Arithmetic is done
 // in the reference's order of operations: `t`,`h` are

@@ -1,0 +1,122 @@
+"""The oracle restatement (oracle/altro_oracle.cpp) against the REFERENCE's own solver code, compiled here from the
+sources under /root/reference by oracle/build_ref.py (on this repo's Eigen stand-in — Eigen itself is absent — and
+driven through oracle/ref_shim/ref_driver.cpp).  Same problem definitions (the reference's examples/problems/*.hpp on
+one side, altro_cpp_b200/problems.py on the other), same perturbed initial states; compared per instance:
+
+* verdict and iteration counts (inner of the last AL iteration, outer, total): exactly — this is the reference's
+  control flow (line-search accept / reject, regularisation, dual and penalty updates, termination tests);
+* cost, stored violation, states and controls: exactly as well.  The oracle was written to perform the reference's
+  operations in the reference's order, and the stand-in evaluates Eigen's expressions in the plain textbook order, so
+  the two agree bit for bit; against a build on the real Eigen (blocked / vectorised products) the last bits of long
+  sums would differ, which is the 1e-12 the reference's one C++-generated golden cost shows (auglag_test.cpp:348).
+
+CPU only.  Skipped where /root/reference is not mounted (the GPU box): oracle/_ref cannot be built there and nothing
+on the GPU path needs it.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from altro_cpp_b200 import problems as P  # noqa: E402
+from oracle import binding as ob  # noqa: E402
+from oracle import build_ref  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not build_ref.available():
+        pytest.skip("the reference sources are not mounted here")
+    return ctypes.CDLL(build_ref.build())
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def ref_solve(lib, entry, first_arg, constrained, x0, n, m, N, options=None):
+    """options: [constraint_tolerance, SetPenalty, initial_penalty, max total, max inner, max outer], < 0 = default"""
+    X = np.zeros((N + 1, n)); U = np.zeros((N, m)); sc = np.zeros(4); it = np.zeros(4, dtype=np.int32)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    opt = None if options is None else np.ascontiguousarray(options, dtype=np.float64)
+    got = getattr(lib, entry)(ctypes.c_int(first_arg), ctypes.c_int(int(constrained)), _ptr(x0), _ptr(opt), _ptr(X),
+                              _ptr(U), _ptr(sc), _ptr(it))
+    assert got == N
+    return dict(X=X, U=U, cost=sc[0], viol=sc[1], max_penalty=sc[2], initial_cost=sc[3], status=int(it[0]),
+                inner=int(it[1]), outer=int(it[2]), total=int(it[3]))
+
+
+def compare(lib, spec, entry, first_arg, constrained, X0, options=None, oracle_options=None):
+    o = ob.solve_batch(spec, X0, options=oracle_options, use_al=constrained, nthreads=8, want_gains=False)
+    same_path, worst = 0, dict(cost=0.0, X=0.0, U=0.0, viol=0.0)
+    for b in range(X0.shape[0]):
+        r = ref_solve(lib, entry, first_arg, constrained, X0[b], spec.n, spec.m, spec.N, options)
+        mine = (int(o["status"][b]), int(o["iters"][b, 0]), int(o["iters"][b, 1]), int(o["iters"][b, 2]))
+        theirs = (r["status"], r["inner"], r["outer"], r["total"])
+        if mine != theirs:
+            continue
+        same_path += 1
+        worst["cost"] = max(worst["cost"], abs(o["cost"][b] - r["cost"]) / max(1.0, abs(r["cost"])))
+        worst["viol"] = max(worst["viol"], abs(o["viol"][b] - r["viol"]))
+        worst["X"] = max(worst["X"], np.abs(o["X"][b] - r["X"]).max())
+        worst["U"] = max(worst["U"], np.abs(o["U"][b] - r["U"]).max())
+    frac = same_path / X0.shape[0]
+    print(f"{spec.name} constrained={constrained}: same verdict and iteration counts {same_path}/{X0.shape[0]}, "
+          f"worst differences among those {worst}")
+    assert frac == 1.0, frac
+    assert worst == dict(cost=0.0, X=0.0, U=0.0, viol=0.0), worst
+    return frac, worst
+
+
+def test_reference_build_reproduces_its_own_golden_values(ref):
+    # test/ilqr/unicycle_ilqr_test.cpp: 9 iterations; test/augmented_lagrangian/auglag_test.cpp:346-350: 14 / 5 and the cost
+    spec = P.unicycle_problem(P.K_TURN90)
+    r = ref_solve(ref, "altro_ref_unicycle", 0, False, spec.x0, 3, 2, 100)
+    assert (r["status"], r["total"]) == (0, 9) and abs(r["initial_cost"] - 259.27636137767087) < 1e-5
+    r = ref_solve(ref, "altro_ref_unicycle", 0, True, spec.x0, 3, 2, 100, [1e-6, -1, -1, -1, -1, -1])
+    assert (r["status"], r["outer"], r["total"]) == (0, 5, 14)
+    assert abs(r["cost"] - 0.03893465058924039) / 0.03893465058924039 < 1e-11 and r["viol"] < 1e-6
+    # perf/benchmark_unicycle.cpp: the three-obstacle solve takes 50 iterations
+    r = ref_solve(ref, "altro_ref_unicycle", 1, True, spec.x0, 3, 2, 100, [-1, 10.0, -1, -1, -1, -1])
+    assert (r["status"], r["total"]) == (0, 50)
+
+
+@pytest.mark.parametrize("scenario,constrained", [(P.K_TURN90, False), (P.K_TURN90, True), (P.K_THREE_OBSTACLES, True)])
+def test_oracle_follows_the_reference_build_unicycle(ref, scenario, constrained):
+    spec = P.unicycle_problem(scenario)
+    X0 = P.perturbed_initial_states(spec, 96, P.UNICYCLE_X0_SCALE)
+    compare(ref, spec, "altro_ref_unicycle", scenario, constrained, X0)
+
+
+def test_oracle_follows_the_reference_build_with_other_options(ref):
+    # tighter tolerance, an explicit SetPenalty with initial_penalty = 0 (so that it is kept), iteration caps
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    X0 = P.perturbed_initial_states(spec, 32, P.UNICYCLE_X0_SCALE, first=1000)
+    o = ob.default_options()
+    o.constraint_tolerance = 1e-6
+    o.initial_penalty = 0.0
+    o.max_iterations_total = 120
+    o.max_iterations_inner = 40
+    for b in range(X0.shape[0]):
+        s = ob.OracleSolver(spec, use_constraints=True, options=o)
+        s.set_initial_state(X0[b])
+        s.set_penalty(25.0)
+        s.solve_al()
+        r = ref_solve(ref, "altro_ref_unicycle", 1, True, X0[b], 3, 2, 100, [1e-6, 25.0, 0.0, 120, 40, -1])
+        st = s.status()
+        assert (st["status"], st["iterations_outer"], st["iterations_total"]) == (r["status"], r["outer"], r["total"]), (b, st, r)
+        X, U = s.trajectory()
+        assert np.array_equal(X, r["X"]) and np.array_equal(U, r["U"])
+        assert s.max_penalty() == r["max_penalty"]
+
+
+@pytest.mark.parametrize("constrained", [False, True])
+def test_oracle_follows_the_reference_build_triple_integrator(ref, constrained):
+    spec = P.triple_integrator_problem(dof=2, N=50, add_constraints=constrained)
+    X0 = P.perturbed_initial_states(spec, 64, P.TRIPLE_INTEGRATOR_X0_SCALE)
+    compare(ref, spec, "altro_ref_triple_integrator", 50, constrained, X0)
