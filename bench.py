@@ -12,8 +12,9 @@ reference's termination, default SolverOptions.
            (pinned host x0 in, X/U/cost/viol/status/iters out, copies inside the timed region)
   roofline = the materialised backward-pass kernel (k_backward_mat) timed live with CUDA events:
            algorithmic bytes (SURVEY.md 8d contract, 37,696 B per instance per pass) / duration
-  cpu_baseline = the CPU oracle (a port of the reference's algorithm; the reference itself cannot
-           be built here — no Eigen) on all host cores over a bounded sample of the same batch
+  cpu_baseline = the CPU oracle (a port of the reference's algorithm, bit-identical to the reference's own sources
+           compiled on this repo's Eigen stand-in — oracle/_ref, tests/test_oracle_vs_reference_build.py — and 8 x
+           faster than that build, so it is the stronger CPU arm) on all host cores over a bounded sample of the batch
 
 `--impl reference` times that CPU path alone (rank 0 only) and prints the same JSON line.
 """
@@ -186,6 +187,33 @@ def cpu_leg_native(workload_name, batch, steps, warmup, sample, nthreads):
         return sample / dt, dt, {"status": d["status"], "iters": d["iters"]}
 
 
+def reference_build_leg(workload_name, spec, X0, count=4):
+    """Single-thread solves/s of oracle/_ref/libaltro_ref.so (the reference's own solver sources compiled on the Eigen
+    stand-in, oracle/build_ref.py) on the first `count` instances, for the workloads its entry point covers; None when
+    the library did not travel or anything goes wrong — this is context for cpu_baseline, never the headline."""
+    try:
+        import ctypes
+        import numpy as np
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libaltro_ref.so")
+        if workload_name != "c2" or not os.path.exists(path):
+            return None
+        lib = ctypes.CDLL(path)
+        n, m, N = spec.n, spec.m, spec.N
+        X = np.zeros((N + 1, n)); U = np.zeros((N, m)); sc = np.zeros(4); it = np.zeros(4, dtype=np.int32)
+        ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        t0 = time.perf_counter()
+        for b in range(count):
+            x0 = np.ascontiguousarray(X0[b], dtype=np.float64)
+            lib.altro_ref_unicycle(ctypes.c_int(1), ctypes.c_int(1), ptr(x0), None, ptr(X), ptr(U), ptr(sc), ptr(it))
+        dt = time.perf_counter() - t0
+        return {"value": count / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                "build": "the reference's altro/**/*.cpp + examples compiled where they lie on this repo's Eigen stand-in "
+                         "(oracle/build_ref.py; Eigen itself is absent from the image), g++ -O2",
+                "sample": f"first {count} instances, one thread ({dt:.1f} s)"}
+    except Exception:  # noqa: BLE001 - context only
+        return None
+
+
 def cpu_child(args):
     spec, gen_x0, default_B, _ = workload(args.workload)
     X0 = gen_x0(spec, args.batch or default_B)
@@ -347,12 +375,14 @@ def main():
             "steps": args.steps, "warmup": W, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl_name, "batch_per_step": sample,
-                       "note": "CPU path of the reference algorithm (oracle port; the reference cannot be "
-                               "built here: Eigen absent), one independent solve per host thread",
+                       "note": "CPU path of the reference algorithm: the oracle port, bit-identical to the reference's own "
+                               "sources built on the Eigen stand-in (oracle/_ref) and faster than that build; one "
+                               "independent solve per host thread",
                        "build": CPU_BUILD},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": "port", "cpu_model": cpu_model(),
                              "build": CPU_BUILD,
-                             "sample": f"first {sample} instances of the {B}-instance batch per step"},
+                             "sample": f"first {sample} instances of the {B}-instance batch per step",
+                             "reference_build": reference_build_leg(args.workload, spec, X0)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -574,6 +604,7 @@ def main():
                "build": CPU_BUILD,
                "sample": f"first {sample} instances of rank 0's batch, one pass ({dt:.1f} s)",
                "single_thread_value": val1, "single_thread_sample": f"first {n1} instances ({dt1:.1f} s)",
+               "reference_build": reference_build_leg(args.workload, spec, X0_host),
                "same_status_and_iterations_as_gpu": agree(out),
                "same_status_and_iterations_as_gpu_native_build": agree(out_native)}
 
