@@ -1,6 +1,8 @@
 """Committed golden vectors (tests/golden/*.npz, produced by tests/golden/make_golden.py with the
-oracle).  CPU: the oracle still reproduces them (guards against silent drift of the
-checker).  GPU: the CUDA path matches them — same iteration path, trajectories to 1e-8."""
+oracle; for c1 / c2 / c3 they are also, number for number, what the reference's own solver sources produce —
+tests/test_oracle_vs_reference_build.py asks oracle/_ref for the same instances).  CPU: the oracle still
+reproduces them (guards against silent drift of the checker).  GPU: the CUDA path matches them — same
+iteration path, trajectories to 1e-8."""
 import glob
 import os
 
