@@ -141,3 +141,85 @@ def test_committed_golden_vectors_are_what_the_reference_build_produces(ref, nam
         for key, got in (("X", r["X"]), ("U", r["U"]), ("cost", r["cost"])):
             want = g[key][b]
             assert np.abs(got - want).max() <= 1e-10 * max(1.0, np.abs(want).max()), (b, key)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Any ProblemSpec on the reference's solver: oracle/ref_shim/ref_driver.cpp replays the builder calls of
+# altro_cpp_b200/problems.py (the same calls build the oracle's and the device's problem) into the reference's own
+# Problem / QuadraticCost / constraint classes.  The cart-pole (C4) and the discrete linear system (C5) are not in
+# the reference: there they are user functors against its ABCs, with the closed forms of the oracle.
+# ---------------------------------------------------------------------------------------------------------------
+def ref_generic(lib, spec, constrained, x0, U0=None, options=None):
+    handle = spec.build(lib, "altro_refb_")
+    n, m, N = spec.n, spec.m, spec.N
+    X = np.zeros((N + 1, n)); U = np.zeros((N, m)); sc = np.zeros(4); it = np.zeros(4, dtype=np.int32)
+    U0 = np.ascontiguousarray(spec.initial_controls() if U0 is None else U0, dtype=np.float64)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    opt = None if options is None else np.ascontiguousarray(options, dtype=np.float64)
+    lib.altro_refb_solve.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 7
+    got = lib.altro_refb_solve(handle, int(constrained), _ptr(x0), _ptr(U0), _ptr(opt), _ptr(X), _ptr(U), _ptr(sc), _ptr(it))
+    lib.altro_refb_problem_destroy.argtypes = [ctypes.c_void_p]
+    lib.altro_refb_problem_destroy(handle)
+    assert got == N
+    return dict(X=X, U=U, cost=sc[0], viol=sc[1], max_penalty=sc[2], status=int(it[0]), inner=int(it[1]),
+                outer=int(it[2]), total=int(it[3]))
+
+
+def compare_generic(lib, spec, constrained, X0, expect_statuses=None):
+    o = ob.solve_batch(spec, X0, use_al=constrained, nthreads=8, want_gains=False)
+    statuses = set()
+    for b in range(X0.shape[0]):
+        r = ref_generic(lib, spec, constrained, X0[b])
+        mine = (int(o["status"][b]), int(o["iters"][b, 0]), int(o["iters"][b, 1]), int(o["iters"][b, 2]))
+        assert mine == (r["status"], r["inner"], r["outer"], r["total"]), (b, mine, r)
+        assert o["cost"][b] == r["cost"] and o["viol"][b] == r["viol"], (b, o["cost"][b], r["cost"])
+        assert np.array_equal(o["X"][b], r["X"]) and np.array_equal(o["U"][b], r["U"]), b
+        statuses.add(r["status"])
+    print(f"{spec.name}: {X0.shape[0]} instances bit-identical; verdicts seen {sorted(statuses)}, "
+          f"iterations {int(o['iters'][:, 2].min())}..{int(o['iters'][:, 2].max())}")
+    if expect_statuses is not None:
+        assert statuses == set(expect_statuses), statuses
+
+
+def test_generic_builder_matches_the_reference_problem_factories(ref):
+    # the replayed ProblemSpec and the reference's own examples/problems/unicycle.cpp give the same solve
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    X0 = P.perturbed_initial_states(spec, 6, P.UNICYCLE_X0_SCALE)
+    for b in range(6):
+        a = ref_generic(ref, spec, True, X0[b])
+        f = ref_solve(ref, "altro_ref_unicycle", 1, True, X0[b], 3, 2, 100)
+        assert (a["status"], a["outer"], a["total"], a["cost"]) == (f["status"], f["outer"], f["total"], f["cost"])
+        assert np.array_equal(a["X"], f["X"]) and np.array_equal(a["U"], f["U"])
+
+
+def test_oracle_follows_the_reference_solver_on_the_cartpole_c4(ref):
+    # BASELINE config C4: 100 inner iterations, kMaxInnerIterations — line-search failures and regularisation at work
+    spec = P.cartpole_problem()
+    compare_generic(ref, spec, True, P.perturbed_initial_states(spec, 10, P.CARTPOLE_X0_SCALE))
+
+
+@pytest.mark.parametrize("literal", [False, True])
+def test_oracle_follows_the_reference_solver_on_the_random_lqr_c5(ref, literal):
+    # BASELINE config C5 (n = 32, m = 8): the m = 8 Cholesky; `literal` is the ill-conditioned variant whose first
+    # backward pass fails its LLT at zero regularisation (restarts, Increase/DecreaseRegularization)
+    spec = P.random_lqr_problem(literal=literal)
+    compare_generic(ref, spec, True, P.normal_initial_states(spec, 6 if literal else 10))
+
+
+def test_oracle_follows_the_reference_solver_on_a_stretched_time_grid(ref):
+    # per-knot steps (Trajectory::SetStep / SetTime): h_k grows along the horizon
+    spec = P.unicycle_problem(P.K_TURN90)
+    N = spec.N
+    h = (np.float32(0.02) + np.float32(0.0002) * np.arange(N + 1, dtype=np.float32)).astype(np.float32)
+    h[N] = 0.0
+    t = np.zeros(N + 1, dtype=np.float32)
+    for k in range(N):
+        t[k + 1] = np.float32(t[k] + h[k])
+    spec.set_steps(t, h)
+    compare_generic(ref, spec, True, P.perturbed_initial_states(spec, 8, P.UNICYCLE_X0_SCALE))
+
+
+def test_oracle_follows_the_reference_solver_on_a_one_dof_triple_integrator(ref):
+    # n = 3, m = 1: the run-time sized instantiation of the reference's templates
+    spec = P.triple_integrator_problem(dof=1, N=30, add_constraints=True)
+    compare_generic(ref, spec, True, P.perturbed_initial_states(spec, 8, (0.5,) * 3))
