@@ -7,6 +7,7 @@
 // the reference's own code; Eigen is absent from this image, so the linear algebra underneath is this repo's
 // Eigen stand-in (altro_cpp_b200/host/include/eigen3/Eigen/Dense: eager evaluation, plain triple loops, unblocked
 // LLT).  Results therefore carry the reference's logic with the stand-in's rounding order.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -31,7 +32,41 @@ struct Outputs {
   double* U;      // [N * m]
   double* scalars;  // cost, max violation, max penalty, initial cost
   int* counters;    // status, iterations_inner, iterations_outer, iterations_total
+  // optional (nullptr = not wanted)
+  double* K = nullptr;     // [N][m * n] column-major, the gains the solve left behind
+  double* d = nullptr;     // [N][m]
+  double* history = nullptr;  // [history_cap][8]: cost, alpha, improvement_ratio, gradient, cost_decrease,
+                              //                  regularization, violations, max_penalty (SolverStats vectors)
+  int history_cap = 0;
+  int* history_rows = nullptr;
 };
+
+template <class Solver>
+void ExportGains(Solver& ilqr, int N, const Outputs& out) {
+  if (out.K == nullptr && out.d == nullptr) return;
+  for (int k = 0; k < N; ++k) {
+    auto& K = ilqr.GetKnotPointFunction(k).GetFeedbackGain();
+    auto& d = ilqr.GetKnotPointFunction(k).GetFeedforwardGain();
+    const int mm = static_cast<int>(K.rows()), nn = static_cast<int>(K.cols());
+    if (out.K != nullptr)
+      for (int j = 0; j < nn; ++j)
+        for (int i = 0; i < mm; ++i) out.K[(k * nn + j) * mm + i] = K(i, j);
+    if (out.d != nullptr)
+      for (int i = 0; i < mm; ++i) out.d[k * mm + i] = d(i);
+  }
+}
+void ExportHistory(const altro::SolverStats& stats, const Outputs& out) {
+  if (out.history == nullptr) return;
+  const std::vector<double>* cols[8] = {&stats.cost, &stats.alpha, &stats.improvement_ratio, &stats.gradient,
+                                        &stats.cost_decrease, &stats.regularization, &stats.violations, &stats.max_penalty};
+  int rows = 0;
+  for (const std::vector<double>* c : cols) rows = std::max(rows, static_cast<int>(c->size()));
+  rows = std::min(rows, out.history_cap);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < 8; ++c)
+      out.history[r * 8 + c] = r < static_cast<int>(cols[c]->size()) ? (*cols[c])[static_cast<std::size_t>(r)] : 0.0;
+  if (out.history_rows != nullptr) *out.history_rows = rows;
+}
 
 template <int n, int m>
 void Export(altro::Trajectory<n, m>& Z, int N, const Outputs& out) {
@@ -71,6 +106,8 @@ void SolveConstrained(const altro::problem::Problem& prob, std::shared_ptr<altro
   out.counters[1] = solver.GetStats().iterations_inner;
   out.counters[2] = solver.GetStats().iterations_outer;
   out.counters[3] = solver.GetStats().iterations_total;
+  ExportGains(solver.GetiLQRSolver(), prob.NumSegments(), out);
+  ExportHistory(solver.GetStats(), out);
 }
 
 template <int n, int m>
@@ -89,6 +126,8 @@ void SolveUnconstrained(const altro::problem::Problem& prob, std::shared_ptr<alt
   out.counters[1] = solver.GetStats().iterations_inner;
   out.counters[2] = 0;
   out.counters[3] = solver.GetStats().iterations_total;
+  ExportGains(solver, prob.NumSegments(), out);
+  ExportHistory(solver.GetStats(), out);
 }
 
 }  // namespace
@@ -350,18 +389,30 @@ int altro_refb_problem_set_initial_state(void* handle, const double* x0) {
   a.x0 = Vec(x0, a.n);
   return 0;
 }
-// one solve of the assembled problem from initial state x0 (nullptr: the problem's) and controls U0 [N][m]
-int altro_refb_solve(void* handle, int constrained, const double* x0, const double* U0, const double* options, double* X,
-                     double* U, double* scalars, int* counters) {
+// one solve of the assembled problem from initial state x0 (nullptr: the problem's) and controls U0 [N][m];
+// K, d, history, history_rows may be nullptr
+int altro_refb_solve_ex(void* handle, int constrained, const double* x0, const double* U0, const double* options, double* X,
+                        double* U, double* scalars, int* counters, double* K, double* d, double* history, int history_cap,
+                        int* history_rows) {
   Assembled& a = *static_cast<Assembled*>(handle);
   if (x0 != nullptr) a.x0 = Vec(x0, a.n);
-  const Outputs out{X, U, scalars, counters};
+  Outputs out{X, U, scalars, counters};
+  out.K = K;
+  out.d = d;
+  out.history = history;
+  out.history_cap = history_cap;
+  out.history_rows = history_rows;
   const bool al = constrained != 0;
   if (a.n == 3 && a.m == 2) SolveAssembled<3, 2>(a, al, U0, options, out);
   else if (a.n == 6 && a.m == 2) SolveAssembled<6, 2>(a, al, U0, options, out);
   else if (a.n == 4 && a.m == 1) SolveAssembled<4, 1>(a, al, U0, options, out);
   else SolveAssembled<Eigen::Dynamic, Eigen::Dynamic>(a, al, U0, options, out);
   return a.N;
+}
+int altro_refb_solve(void* handle, int constrained, const double* x0, const double* U0, const double* options, double* X,
+                     double* U, double* scalars, int* counters) {
+  return altro_refb_solve_ex(handle, constrained, x0, U0, options, X, U, scalars, counters, nullptr, nullptr, nullptr, 0,
+                             nullptr);
 }
 
 }  // extern "C"

@@ -223,3 +223,45 @@ def test_oracle_follows_the_reference_solver_on_a_one_dof_triple_integrator(ref)
     # n = 3, m = 1: the run-time sized instantiation of the reference's templates
     spec = P.triple_integrator_problem(dof=1, N=30, add_constraints=True)
     compare_generic(ref, spec, True, P.perturbed_initial_states(spec, 8, (0.5,) * 3))
+
+
+def ref_generic_ex(lib, spec, constrained, x0, options=None, history_cap=400):
+    handle = spec.build(lib, "altro_refb_")
+    n, m, N = spec.n, spec.m, spec.N
+    X = np.zeros((N + 1, n)); U = np.zeros((N, m)); sc = np.zeros(4); it = np.zeros(4, dtype=np.int32)
+    K = np.zeros((N, n, m)); d = np.zeros((N, m)); hist = np.zeros((history_cap, 8)); rows = ctypes.c_int(0)
+    U0 = np.ascontiguousarray(spec.initial_controls(), dtype=np.float64)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    opt = None if options is None else np.ascontiguousarray(options, dtype=np.float64)
+    lib.altro_refb_solve_ex.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 10 + [ctypes.c_int, ctypes.c_void_p]
+    lib.altro_refb_solve_ex(handle, int(constrained), _ptr(x0), _ptr(U0), _ptr(opt), _ptr(X), _ptr(U), _ptr(sc), _ptr(it),
+                            _ptr(K), _ptr(d), _ptr(hist), history_cap, ctypes.byref(rows))
+    lib.altro_refb_problem_destroy.argtypes = [ctypes.c_void_p]
+    lib.altro_refb_problem_destroy(handle)
+    return dict(X=X, U=U, K=np.ascontiguousarray(K.transpose(0, 2, 1)), d=d, history=hist[:rows.value], cost=sc[0])
+
+
+@pytest.mark.parametrize("config", ["unicycle-3obs", "triple-integrator", "unicycle-ilqr"])
+def test_gains_and_solver_stats_vectors_match_the_reference_build(ref, config):
+    """The feedback / feed-forward gains a solve leaves behind and the per-iteration SolverStats vectors (cost, alpha,
+    improvement_ratio, gradient, cost_decrease, regularization, violations, max_penalty; solver_stats.hpp:54-61, with
+    the carry-forward rows of Log / NewIteration) — the device is tested against the oracle's on both counts."""
+    constrained = config != "unicycle-ilqr"
+    if config == "triple-integrator":
+        spec = P.triple_integrator_problem(dof=2, N=50, add_constraints=True)
+        X0 = P.perturbed_initial_states(spec, 6, P.TRIPLE_INTEGRATOR_X0_SCALE)
+    else:
+        spec = P.unicycle_problem(P.K_THREE_OBSTACLES if constrained else P.K_TURN90)
+        X0 = P.perturbed_initial_states(spec, 6, P.UNICYCLE_X0_SCALE)
+    names = ("cost", "alpha", "z", "gradient", "cost_decrease", "regularization", "violations", "max_penalty")
+    for b in range(X0.shape[0]):
+        r = ref_generic_ex(ref, spec, constrained, X0[b])
+        s = ob.OracleSolver(spec, use_constraints=constrained)
+        s.set_initial_state(X0[b])
+        (s.solve_al if constrained else s.solve_ilqr)()
+        K, d = s.gains()
+        assert np.array_equal(K, r["K"]) and np.array_equal(d, r["d"]), b
+        for col, name in enumerate(names):
+            mine = s.stat(name)
+            assert mine.shape[0] == r["history"].shape[0], (b, name, mine.shape, r["history"].shape)
+            assert np.array_equal(mine, r["history"][:, col]), (b, name)
