@@ -89,14 +89,21 @@ void Apply(altro::SolverOptions& o, const double* options) {
   if (options[5] >= 0) o.max_iterations_outer = static_cast<int>(options[5]);
 }
 
+// warm_solves: that many further Solve() calls on the same solver, each starting from the previous solution with
+// reset_duals = false and initial_penalty = 0 (the MPC-style re-solve of docs/Overview.dox:49-54 there)
 template <int n, int m>
 void SolveConstrained(const altro::problem::Problem& prob, std::shared_ptr<altro::Trajectory<n, m>> Z, const double* options,
-                      const Outputs& out) {
+                      const Outputs& out, int warm_solves = 0) {
   altro::augmented_lagrangian::AugmentedLagrangianiLQR<n, m> solver(prob);
   solver.SetTrajectory(Z);
   Apply(solver.GetOptions(), options);
   if (options != nullptr && options[1] >= 0) solver.SetPenalty(options[1]);
   solver.Solve();
+  for (int again = 0; again < warm_solves; ++again) {
+    solver.GetOptions().reset_duals = false;
+    solver.GetOptions().initial_penalty = 0.0;
+    solver.Solve();
+  }
   Export<n, m>(*Z, prob.NumSegments(), out);
   out.scalars[1] = solver.GetMaxViolation();  // of the constraint values the solve left behind: before Cost() refreshes them
   out.scalars[2] = solver.GetMaxPenalty();
@@ -284,7 +291,8 @@ VectorXd Vec(const double* p, int len) {
 }
 
 template <int n, int m>
-void SolveAssembled(Assembled& a, bool constrained, const double* U0, const double* options, const Outputs& out) {
+void SolveAssembled(Assembled& a, bool constrained, const double* U0, const double* options, const Outputs& out,
+                    int warm_solves = 0) {
   auto Z = std::make_shared<altro::Trajectory<n, m>>(a.n, a.m, a.N);
   for (int k = 0; k <= a.N; ++k) {
     Z->SetStep(k, a.h[k]);
@@ -293,7 +301,7 @@ void SolveAssembled(Assembled& a, bool constrained, const double* U0, const doub
   for (int k = 0; k < a.N; ++k)
     for (int i = 0; i < a.m; ++i) Z->Control(k)(i) = U0 != nullptr ? U0[k * a.m + i] : 0.0;
   a.prob.SetInitialState(a.x0);
-  if (constrained) SolveConstrained<n, m>(a.prob, Z, options, out);
+  if (constrained) SolveConstrained<n, m>(a.prob, Z, options, out, warm_solves);
   else SolveUnconstrained<n, m>(a.prob, Z, options, out);
 }
 
@@ -407,6 +415,17 @@ int altro_refb_solve_ex(void* handle, int constrained, const double* x0, const d
   else if (a.n == 6 && a.m == 2) SolveAssembled<6, 2>(a, al, U0, options, out);
   else if (a.n == 4 && a.m == 1) SolveAssembled<4, 1>(a, al, U0, options, out);
   else SolveAssembled<Eigen::Dynamic, Eigen::Dynamic>(a, al, U0, options, out);
+  return a.N;
+}
+// an AL solve followed by `warm_solves` warm-started re-solves on the same solver; outputs are those of the last one
+int altro_refb_solve_warm(void* handle, const double* x0, const double* U0, const double* options, int warm_solves,
+                          double* X, double* U, double* scalars, int* counters) {
+  Assembled& a = *static_cast<Assembled*>(handle);
+  if (x0 != nullptr) a.x0 = Vec(x0, a.n);
+  const Outputs out{X, U, scalars, counters};
+  if (a.n == 3 && a.m == 2) SolveAssembled<3, 2>(a, true, U0, options, out, warm_solves);
+  else if (a.n == 6 && a.m == 2) SolveAssembled<6, 2>(a, true, U0, options, out, warm_solves);
+  else SolveAssembled<Eigen::Dynamic, Eigen::Dynamic>(a, true, U0, options, out, warm_solves);
   return a.N;
 }
 int altro_refb_solve(void* handle, int constrained, const double* x0, const double* U0, const double* options, double* X,

@@ -265,3 +265,36 @@ def test_gains_and_solver_stats_vectors_match_the_reference_build(ref, config):
             mine = s.stat(name)
             assert mine.shape[0] == r["history"].shape[0], (b, name, mine.shape, r["history"].shape)
             assert np.array_equal(mine, r["history"][:, col]), (b, name)
+
+
+def test_warm_started_resolve_matches_the_reference_build(ref):
+    """MPC-style re-solve (docs/Overview.dox:49-54 there; solver_options.hpp:47-48): a second and a third Solve() on the
+    same solver, from the previous solution, with reset_duals = false and initial_penalty = 0 — multipliers and
+    penalties carry over (al_solver.hpp:292-297).  The device's warm start is tested against the oracle's."""
+    spec = P.unicycle_problem(P.K_THREE_OBSTACLES)
+    X0 = P.perturbed_initial_states(spec, 8, P.UNICYCLE_X0_SCALE)
+    n, m, N = spec.n, spec.m, spec.N
+    ref.altro_refb_solve_warm.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] + [ctypes.c_void_p] * 4
+    ref.altro_refb_problem_destroy.argtypes = [ctypes.c_void_p]
+    for b in range(X0.shape[0]):
+        for warm in (1, 2):
+            handle = spec.build(ref, "altro_refb_")
+            X = np.zeros((N + 1, n)); U = np.zeros((N, m)); sc = np.zeros(4); it = np.zeros(4, dtype=np.int32)
+            U0 = np.ascontiguousarray(spec.initial_controls(), dtype=np.float64)
+            x0 = np.ascontiguousarray(X0[b], dtype=np.float64)
+            ref.altro_refb_solve_warm(handle, _ptr(x0), _ptr(U0), None, warm, _ptr(X), _ptr(U), _ptr(sc), _ptr(it))
+            ref.altro_refb_problem_destroy(handle)
+            s = ob.OracleSolver(spec, use_constraints=True)
+            s.set_initial_state(X0[b])
+            s.solve_al()
+            o = ob.default_options()
+            o.reset_duals = 0
+            o.initial_penalty = 0.0
+            s.set_options(o)
+            for _ in range(warm):
+                s.solve_al()
+            st = s.status()
+            assert (st["status"], st["iterations_inner"], st["iterations_outer"], st["iterations_total"]) == tuple(int(v) for v in it), (b, warm, st, it)
+            Xo, Uo = s.trajectory()
+            assert np.array_equal(Xo, X) and np.array_equal(Uo, U), (b, warm)
+            assert s.max_penalty() == sc[2]
