@@ -315,7 +315,8 @@ def random_lqr_problem(n: int = 32, m: int = 8, N: int = 100, seed: int = 5,
                        literal: bool = False) -> ProblemSpec:
     """BASELINE config C5: discrete LTI x+ = A x + B u, A = I + g G/sqrt(n),
     B = 0.1 H, G, H i.i.d. N(0,1) from `seed`; Q = I h, Qf = 10 I, h = 0.05; unconstrained.
-    Not in the reference: parity is GPU vs oracle only.
+    Not in the reference: parity is GPU vs oracle, and the oracle vs the reference's own solver run on a linear
+    functor (tests/test_oracle_vs_reference_build.py).
 
     literal=True takes SURVEY.md's numbers verbatim (g = 0.05, R = 0.1 h I).  That problem is
     ill-conditioned (spectral radius 1.05 over 100 steps, cond(Quu) ~ 1e8): the first backward pass

@@ -1,7 +1,8 @@
 """Generates tests/golden/*.npz with the CPU oracle (which itself is pinned to the reference's
-known-answer tests, tests/test_oracle_golden.py).  The reference cannot be built or imported in
-this image (C++/Eigen), so these fixtures are oracle outputs, not reference outputs; they let the
-GPU tests check the CUDA path against committed vectors without running the oracle.
+known-answer tests, tests/test_oracle_golden.py).  The fixtures are oracle outputs; for c1, c2 and c3 they are
+also, number for number, the outputs of the reference's own solver sources compiled on the Eigen stand-in
+(oracle/build_ref.py; checked by tests/test_oracle_vs_reference_build.py).  They let the GPU tests check the
+CUDA path against committed vectors without running the oracle.
 
     python tests/golden/make_golden.py
 """

@@ -310,7 +310,9 @@ def test_solve_triple_integrator_al(gpu, oracle):
 
 
 def test_solve_cartpole_al(gpu, oracle):
-    # BASELINE config C4 (model not in the reference: parity is GPU vs oracle only)
+    # BASELINE config C4 (model not in the reference: GPU vs oracle here; the oracle equals the reference's own
+    # solver run on a cart-pole functor, tests/test_oracle_vs_reference_build.py, and
+    # tests/test_gpu_vs_reference_build.py compares the device with that directly)
     spec = P.cartpole_problem(N=200)
     X0 = P.perturbed_initial_states(spec, 64, P.CARTPOLE_X0_SCALE)
     errs, frac, r, ref = compare_batch(gpu, oracle, spec, X0)
@@ -539,7 +541,8 @@ def test_solve_triple_integrator_full_c3_slice(gpu, oracle):
 @pytest.mark.parametrize("literal", [False, True])
 def test_solve_random_lqr_c5(gpu, oracle, literal):
     # BASELINE config C5: n = 32, m = 8, N = 100, unconstrained.  The model is not in the reference: parity
-    # is GPU vs oracle only.  Two kernels, selected by the engine:
+    # is GPU vs oracle here (the oracle equals the reference's own solver run on a linear functor,
+    # tests/test_oracle_vs_reference_build.py).  Two kernels, selected by the engine:
     #   fused  -> large.cuh, one instance per CTA, no FMA contraction, sums in the oracle's order: bit-equal;
     #   phased -> large_mma.cuh (the default), one instance per warp on mma.sync.m8n8k4.f64: equal to rounding.
     # literal=True is the ill-conditioned variant whose LLT decisions hinge on the last bit (problems.py):
