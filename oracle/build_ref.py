@@ -7,8 +7,7 @@ run here and DESIGN.md records the reference as not buildable as shipped.  This 
 stand-in of the host mirror instead (altro_cpp_b200/host/include/eigen3/Eigen/Dense) — include order puts
 /root/reference first, so every `altro/...` header is the reference's and only `eigen3/Eigen/Dense` comes from this
 repo — and force-includes oracle/ref_shim/compat.hpp (fmt formatter specialisations for the newer fmt of this image).
-Left out: altro/main.cpp (a demo main) and altro/common/functionbase.cpp (the derivative checkers, not on the solve
-path; they use Eigen's implicit 1x1-product-to-scalar conversion, which the stand-in does not have).
+Left out: altro/main.cpp (a demo main).
 
 The result is the reference's control flow and formulas on the stand-in's linear algebra: a cross-check of the oracle
 restatement's logic (status, iteration counts, line-search decisions, AL updates), not of Eigen's rounding order.
@@ -28,7 +27,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference"
 OUT = os.path.join(ROOT, "oracle", "_ref")
 LIB = os.path.join(OUT, "libaltro_ref.so")
-SKIP = {"altro/main.cpp", "altro/common/functionbase.cpp"}
+SKIP = {"altro/main.cpp"}
 
 
 def fmt_include():
