@@ -45,18 +45,37 @@ def _flags():
             "-I", build_ref.fmt_include(), f'-DLOCAL_LOG_DIR="{OUT}"', f'-DLOGDIR="{OUT}"']   # no -DNDEBUG: death tests
 
 
+def _compile_one(src):
+    obj = os.path.join(OUT, os.path.relpath(src, "/").replace("/", "_") + ".o")
+    if os.path.exists(obj) and os.path.getmtime(obj) >= os.path.getmtime(src):
+        return obj
+    r = subprocess.run(_flags() + ["-c", src, "-o", obj], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise subprocess.CalledProcessError(r.returncode, src, output=r.stdout + r.stderr)
+    return obj
+
+
+def reference_objects(jobs=8):
+    """the reference's solver and example sources compiled (assertions on) for linking into test programs"""
+    os.makedirs(OUT, exist_ok=True)
+    sources = [s for s in build_ref.sources() if not s.endswith("ref_driver.cpp")]
+    with ThreadPoolExecutor(max_workers=jobs) as pool:
+        return list(pool.map(_compile_one, sources))
+
+
+def build_program(src, name):
+    """one program of this repo (a probe) against the reference's own headers and sources -> executable path"""
+    exe = os.path.join(OUT, name)
+    subprocess.check_call(_flags() + [src] + reference_objects() + ["-o", exe, "-lpthread"])
+    return exe
+
+
 def build_all(jobs=8):
     """-> {rel: (exe or None, log)}"""
     os.makedirs(OUT, exist_ok=True)
     sources = [s for s in build_ref.sources() if not s.endswith("ref_driver.cpp")]
     sources.append(os.path.join(ref_unit.STANDIN, "gtest_main.cc"))
-
-    def compile_one(src):
-        obj = os.path.join(OUT, os.path.relpath(src, "/").replace("/", "_") + ".o")
-        r = subprocess.run(_flags() + ["-c", src, "-o", obj], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise subprocess.CalledProcessError(r.returncode, src, output=r.stdout + r.stderr)
-        return obj
+    compile_one = _compile_one
 
     def link_one(rel):
         exe = os.path.join(OUT, rel.replace("/", "_").replace(".cpp", ""))
