@@ -127,3 +127,46 @@ def test_mirror_covers_the_reference_header_tree():
             if f.endswith(".hpp") and rel not in mine:
                 missing.append(rel)
     assert not missing, missing
+
+
+def test_mirror_offers_the_public_methods_of_the_reference_headers():
+    """Every method the reference's headers declare in a public section has a counterpart of the same name in the
+    mirror header of the same path.  A name-level audit (signatures are exercised by compiling the reference's own
+    programs and tests): it catches a method that was never offered."""
+    import re
+    ref = "/root/reference/altro"
+    if not os.path.isdir(ref):
+        pytest.skip("the reference sources are not mounted here")
+    decl = re.compile(r"^  (?:template\s*<[^>]*>\s*)?(?:static\s+|virtual\s+|explicit\s+|inline\s+|constexpr\s+)*"
+                      r"[A-Za-z_:<>,&\*\s]*?\b([A-Z][A-Za-z0-9]*)\s*\(")
+    # calls inside inline bodies that the line-based scan picks up, private helpers, and one method the reference
+    # declares but never defines (FunctionBase::TestCheck)
+    not_api = {"TestCheck", "DefaultLogger", "SetData", "Init", "CalcIndividualCosts", "DecreaseRegularization",
+               "IncreaseRegularization"}
+    # public in the reference, deliberately not offered (DESIGN.md §3.7): one line-search candidate on the host-visible
+    # buffer Zbar_, and the device half of SolveSetup()
+    not_offered = {"ilqr/ilqr.hpp": {"RolloutClosedLoop", "ResetInternalVariables"}}
+    missing = {}
+    for d, _, files in os.walk(ref):
+        for f in files:
+            if not f.endswith(".hpp"):
+                continue
+            rel = os.path.relpath(os.path.join(d, f), ref)
+            mirror = open(os.path.join(HOST, "altro", rel)).read()
+            public = False
+            names = set()
+            for line in open(os.path.join(d, f)):
+                if re.match(r"^ public:", line):
+                    public = True
+                elif re.match(r"^ (private|protected):", line):
+                    public = False
+                elif re.match(r"^(class|struct)\b", line):
+                    public = line.startswith("struct")
+                elif public and not line.strip().startswith(("//", "*", "return", "ALTRO_")):
+                    m = decl.match(line)
+                    if m:
+                        names.add(m.group(1))
+            gone = sorted(n for n in names - not_api - not_offered.get(rel, set()) if not re.search(r"\b" + n + r"\b", mirror))
+            if gone:
+                missing[rel] = gone
+    assert not missing, missing
