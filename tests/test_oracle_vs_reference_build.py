@@ -298,3 +298,80 @@ def test_warm_started_resolve_matches_the_reference_build(ref):
             Xo, Uo = s.trajectory()
             assert np.array_equal(Xo, X) and np.array_equal(Uo, U), (b, warm)
             assert s.max_penalty() == sc[2]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Fuzz: random problems (horizon, weights, goal, control bounds with infinite sides, 0-3 circular obstacles, uniform or
+# jittered time grids, initial controls), random termination options; every one must come out of the oracle exactly
+# as it comes out of the reference's own solver — whatever the verdict.
+# ---------------------------------------------------------------------------------------------------------------
+def random_unicycle_problem(rng):
+    import math
+    N = int(rng.integers(8, 60))
+    n, m = 3, 2
+    spec = P.ProblemSpec(n, m, N, name=f"fuzz-unicycle-N{N}")
+    spec.set_model(P.MODEL_UNICYCLE, [])
+    h = np.float32(np.float32(rng.uniform(1.0, 4.0)) / np.float32(N))
+    if rng.random() < 0.5:
+        spec.set_uniform_step(h)
+    else:
+        hs = (h * (1 + 0.3 * rng.uniform(-1, 1, N + 1))).astype(np.float32)
+        hs[N] = 0
+        t = np.zeros(N + 1, dtype=np.float32)
+        for k in range(N):
+            t[k + 1] = np.float32(t[k] + hs[k])
+        spec.set_steps(t, hs)
+    Q = np.diag(rng.uniform(1e-3, 1.0, n)); R = np.diag(rng.uniform(1e-3, 1.0, m)); Qf = np.diag(rng.uniform(1.0, 500.0, n))
+    xf = np.array([rng.uniform(0.5, 2.5), rng.uniform(0.5, 2.5), rng.uniform(-math.pi, math.pi)])
+    uref = rng.uniform(-0.2, 0.2, m)
+    spec.set_cost(0, N, *P.lqr_cost(Q, R, xf, uref))
+    spec.set_cost(N, N + 1, *P.lqr_cost(Qf, R * 0, xf, uref))
+    obstacles = int(rng.integers(0, 4))
+    cx, cy, cr = rng.uniform(0.2, 2.2, obstacles), rng.uniform(0.2, 2.2, obstacles), rng.uniform(0.05, 0.35, obstacles)
+    lb = np.array([rng.uniform(-1.0, 0.0), -rng.uniform(0.5, 3.0)])
+    ub = np.array([rng.uniform(0.8, 3.0), rng.uniform(0.5, 3.0)])
+    if rng.random() < 0.3:
+        lb[0] = -np.inf
+    if rng.random() < 0.2:
+        ub[1] = np.inf
+    for k in range(N):
+        if obstacles and k >= 1:
+            spec.add_circles(k, cx, cy, cr)
+        spec.add_control_bound(k, lb, ub)
+    if rng.random() < 0.8:
+        spec.add_goal(N, xf)
+    spec.set_initial_state(np.zeros(n))
+    spec.u0 = rng.uniform(-0.3, 0.5, m)
+    spec.xf = xf
+    return spec
+
+
+def test_fuzzed_problems_come_out_of_the_oracle_as_out_of_the_reference_solver(ref):
+    rng = np.random.default_rng(20251017)
+    verdicts = {}
+    for trial in range(160):
+        spec = random_unicycle_problem(rng)
+        x0 = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), rng.uniform(-0.6, 0.6)])
+        o = ob.default_options()
+        opts = [-1.0] * 6
+        if rng.random() < 0.5:
+            o.constraint_tolerance = opts[0] = float(10 ** rng.uniform(-7, -3))
+        if rng.random() < 0.3:
+            o.max_iterations_total = int(rng.integers(5, 60)); opts[3] = o.max_iterations_total
+        if rng.random() < 0.3:
+            o.max_iterations_inner = int(rng.integers(3, 30)); opts[4] = o.max_iterations_inner
+        if rng.random() < 0.3:
+            o.max_iterations_outer = int(rng.integers(1, 6)); opts[5] = o.max_iterations_outer
+        s = ob.OracleSolver(spec, use_constraints=True, options=o)
+        s.set_initial_state(x0)
+        s.solve_al()
+        st = s.status()
+        X, U = s.trajectory()
+        r = ref_generic(ref, spec, True, x0, options=opts)
+        mine = (st["status"], st["iterations_inner"], st["iterations_outer"], st["iterations_total"])
+        assert mine == (r["status"], r["inner"], r["outer"], r["total"]), (trial, spec.name, st, r)
+        assert np.array_equal(X, r["X"]) and np.array_equal(U, r["U"]) and s.cost() == r["cost"], (trial, spec.name)
+        verdicts[r["status"]] = verdicts.get(r["status"], 0) + 1
+    print("verdicts seen (SolverStatus -> count):", dict(sorted(verdicts.items())))
+    # solved, hit the total / outer / inner iteration limits, ran into the maximum penalty
+    assert set(verdicts) >= {0, 5, 6, 7, 8}, verdicts
