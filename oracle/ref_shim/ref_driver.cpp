@@ -79,8 +79,21 @@ void Export(altro::Trajectory<n, m>& Z, int N, const Outputs& out) {
 
 // options: [0] constraint_tolerance, [1] SetPenalty value, [2] initial_penalty, [3] max_iterations_total,
 //          [4] max_iterations_inner, [5] max_iterations_outer; a negative entry keeps the reference's default
+// further option overrides, set once for all following solves (altro_ref_set_extra_options; not thread-safe — the
+// tests that use it solve one problem at a time): state_max, control_max, bp_reg_max, bp_reg_fail_threshold,
+// line_search_max_iterations, cost_tolerance, gradient_tolerance, bp_reg_initial; negative = the reference's default
+double g_extra[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+
 void Apply(altro::SolverOptions& o, const double* options) {
   o.verbose = altro::LogLevel::kSilent;
+  if (g_extra[0] >= 0) o.state_max = g_extra[0];
+  if (g_extra[1] >= 0) o.control_max = g_extra[1];
+  if (g_extra[2] >= 0) o.bp_reg_max = g_extra[2];
+  if (g_extra[3] >= 0) o.bp_reg_fail_threshold = static_cast<int>(g_extra[3]);
+  if (g_extra[4] >= 0) o.line_search_max_iterations = static_cast<int>(g_extra[4]);
+  if (g_extra[5] >= 0) o.cost_tolerance = g_extra[5];
+  if (g_extra[6] >= 0) o.gradient_tolerance = g_extra[6];
+  if (g_extra[7] >= 0) o.bp_reg_initial = g_extra[7];
   if (options == nullptr) return;
   if (options[0] >= 0) o.constraint_tolerance = options[0];
   if (options[2] >= 0) o.initial_penalty = options[2];
@@ -140,6 +153,10 @@ void SolveUnconstrained(const altro::problem::Problem& prob, std::shared_ptr<alt
 }  // namespace
 
 extern "C" {
+
+void altro_ref_set_extra_options(const double* extra) {
+  for (int i = 0; i < 8; ++i) g_extra[i] = extra != nullptr ? extra[i] : -1.0;
+}
 
 // examples/problems/unicycle.hpp: scenario 0 = kTurn90, 1 = kThreeObstacles; N = 100
 int altro_ref_unicycle(int scenario, int constrained, const double* x0, const double* options, double* X, double* U,

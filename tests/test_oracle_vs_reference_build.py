@@ -375,3 +375,78 @@ def test_fuzzed_problems_come_out_of_the_oracle_as_out_of_the_reference_solver(r
     print("verdicts seen (SolverStatus -> count):", dict(sorted(verdicts.items())))
     # solved, hit the total / outer / inner iteration limits, ran into the maximum penalty
     assert set(verdicts) >= {0, 5, 6, 7, 8}, verdicts
+
+
+def _set_extra(lib, extra):
+    """state_max, control_max, bp_reg_max, bp_reg_fail_threshold, line_search_max_iterations, cost_tolerance,
+    gradient_tolerance, bp_reg_initial for all following reference solves (None: back to the defaults)"""
+    if extra is None:
+        lib.altro_ref_set_extra_options(None)
+    else:
+        e = np.ascontiguousarray(extra, dtype=np.float64)
+        lib.altro_ref_set_extra_options(e.ctypes.data_as(ctypes.c_void_p))
+
+
+def test_fuzzed_limits_and_line_search_options(ref):
+    """state / control limits in the forward pass (kStateLimit, kControlLimit), short line searches, other convergence
+    tolerances: the rarely taken branches of ilqr.hpp:468-558."""
+    rng = np.random.default_rng(7)
+    verdicts = {}
+    try:
+        for trial in range(160):
+            spec = random_unicycle_problem(rng)
+            x0 = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), rng.uniform(-0.6, 0.6)])
+            o = ob.default_options()
+            extra = [-1.0] * 8
+            mode = trial % 4
+            if mode == 0:
+                o.state_max = extra[0] = float(rng.uniform(1.0, 3.5))
+            elif mode == 1:
+                o.control_max = extra[1] = float(rng.uniform(0.5, 3.0))
+            elif mode == 2:
+                o.line_search_max_iterations = int(rng.integers(1, 5)); extra[4] = o.line_search_max_iterations
+            else:
+                o.cost_tolerance = extra[5] = float(10 ** rng.uniform(-8, -2))
+                o.gradient_tolerance = extra[6] = float(10 ** rng.uniform(-5, -1))
+            _set_extra(ref, extra)
+            s = ob.OracleSolver(spec, use_constraints=True, options=o)
+            s.set_initial_state(x0)
+            s.solve_al()
+            st = s.status()
+            X, U = s.trajectory()
+            r = ref_generic(ref, spec, True, x0)
+            mine = (st["status"], st["iterations_inner"], st["iterations_outer"], st["iterations_total"])
+            assert mine == (r["status"], r["inner"], r["outer"], r["total"]), (trial, mode, st, r)
+            assert np.array_equal(X, r["X"]) and np.array_equal(U, r["U"]), (trial, mode)
+            verdicts[r["status"]] = verdicts.get(r["status"], 0) + 1
+    finally:
+        _set_extra(ref, None)
+    print("verdicts seen (SolverStatus -> count):", dict(sorted(verdicts.items())))
+    assert set(verdicts) >= {0, 2, 3, 7}, verdicts
+
+
+def test_capped_regularisation_on_the_ill_conditioned_lqr(ref):
+    """C5 'literal': the first backward pass fails its Cholesky; with bp_reg_max capped the regularisation saturates
+    (ilqr.hpp:401-442, :770-786) and the solve takes another route — the same one in the oracle."""
+    spec = P.random_lqr_problem(literal=True)
+    X0 = P.normal_initial_states(spec, 3)
+    try:
+        for reg_max, threshold in [(1e-10, 1), (1e-9, 2), (1e-3, 5)]:
+            o = ob.default_options()
+            o.bp_reg_max = reg_max
+            o.bp_reg_fail_threshold = threshold
+            extra = [-1.0] * 8
+            extra[2], extra[3] = reg_max, threshold
+            _set_extra(ref, extra)
+            for b in range(X0.shape[0]):
+                s = ob.OracleSolver(spec, use_constraints=True, options=o)
+                s.set_initial_state(X0[b])
+                s.solve_al()
+                st = s.status()
+                X, U = s.trajectory()
+                r = ref_generic(ref, spec, True, X0[b])
+                mine = (st["status"], st["iterations_inner"], st["iterations_outer"], st["iterations_total"])
+                assert mine == (r["status"], r["inner"], r["outer"], r["total"]), (reg_max, threshold, b, st, r)
+                assert np.array_equal(X, r["X"]) and np.array_equal(U, r["U"]), (reg_max, threshold, b)
+    finally:
+        _set_extra(ref, None)
