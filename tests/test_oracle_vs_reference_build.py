@@ -450,3 +450,44 @@ def test_capped_regularisation_on_the_ill_conditioned_lqr(ref):
                 assert np.array_equal(X, r["X"]) and np.array_equal(U, r["U"]), (reg_max, threshold, b)
     finally:
         _set_extra(ref, None)
+
+
+def test_fuzzed_triple_integrators_and_cartpoles(ref):
+    """random triple integrators (one and two degrees of freedom: n = 3 and n = 6) with control bounds and a goal, and
+    cart-poles over random horizons, default options"""
+    rng = np.random.default_rng(11)
+    verdicts = {}
+    for trial in range(60):
+        if trial % 3 < 2:
+            dof = int(rng.integers(1, 3))
+            n, m, N = 3 * dof, dof, int(rng.integers(5, 60))
+            spec = P.ProblemSpec(n, m, N, name=f"fuzz-triple-integrator-dof{dof}-N{N}")
+            spec.set_model(P.MODEL_TRIPLE_INTEGRATOR, [])
+            spec.set_uniform_step(np.float32(rng.uniform(0.02, 0.2)))
+            Q = np.diag(rng.uniform(0.01, 2.0, n)); R = np.diag(rng.uniform(1e-4, 0.1, m)); Qf = np.diag(rng.uniform(10, 1e5, n))
+            xf = np.concatenate([rng.uniform(-2, 2, dof), np.zeros(2 * dof)])
+            spec.set_cost(0, N, *P.lqr_cost(Q, R, xf, np.zeros(m)))
+            spec.set_cost(N, N + 1, *P.lqr_cost(Qf, R * 0, xf, np.zeros(m)))
+            ub = rng.uniform(1, 200, m)
+            for k in range(N):
+                spec.add_control_bound(k, -ub, ub)
+            if rng.random() < 0.8:
+                spec.add_goal(N, xf)
+            spec.set_initial_state(np.zeros(n))
+            spec.u0 = np.zeros(m)
+            spec.xf = xf
+            x0 = rng.uniform(-1.5, 1.5, n)
+        else:
+            spec = P.cartpole_problem(N=int(rng.integers(20, 120)))
+            x0 = rng.uniform(-0.2, 0.2, 4)
+        s = ob.OracleSolver(spec, use_constraints=True)
+        s.set_initial_state(x0)
+        s.solve_al()
+        st = s.status()
+        X, U = s.trajectory()
+        r = ref_generic(ref, spec, True, x0)
+        mine = (st["status"], st["iterations_inner"], st["iterations_outer"], st["iterations_total"])
+        assert mine == (r["status"], r["inner"], r["outer"], r["total"]), (trial, spec.name, st, r)
+        assert np.array_equal(X, r["X"]) and np.array_equal(U, r["U"]), (trial, spec.name)
+        verdicts[r["status"]] = verdicts.get(r["status"], 0) + 1
+    print("verdicts seen (SolverStatus -> count):", dict(sorted(verdicts.items())))
